@@ -1,0 +1,416 @@
+#!/usr/bin/env python3
+"""bench.py -- k-mers/s scanned by the hetmers hot path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path
+  python bench.py --impl reference ...                     the reference's own C hetmers on host cores
+
+A "step" is one full scan (pass 1 + degree exchange + pass 2 + plot reduce = T_scan of SURVEY.md
+§8d) of one synthetic FastK table.  Workload = BASELINE.json configs[1]: synthetic diploid k=31
+table, het 1 %, coverage 40x, L=12, ~2e8 k-mers per GPU (weak scaling: with N GPUs the table has
+N x 2e8 k-mers, every rank holds a replica and scans a contiguous 1/N index range).
+
+  value  k-mers/s with the table already unpacked in HBM (CUDA events, max over ranks)
+  e2e    k-mers/s through the public C-ABI call hm_hetmers_host() on HOST buffers holding the raw
+         FastK part payloads in pinned memory: H2D + unpack + bucket index + both passes + plot D2H
+  roofline   pass-1 kernel (dominant): algorithmic bytes A = 2*TBYTE+2 = 22 B/k-mer
+             x k-mers per launch / average launch time, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the reference C hetmers (oracle/_ref/hetmers; else the oracle port) on the host
+             cores, on a bounded sample of the same workload
+Inputs (1.9 GB table + 0.27 GB bucket index per 2e8 k-mers) exceed the 126 MB L2, so no flush is
+needed between timed iterations.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K, PLOIDY, HET, COV, LCUT, SEED = 31, 2, 0.01, 40.0, 12, 2
+ALGO_BYTES_PER_KMER = 2 * ((K + 3) // 4 + 2) + 2          # 22 B at k=31
+METRIC = "k-mers/sec scanned (hetmers)"
+UNIT = "k-mers/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nels", type=float, default=2e8, help="target k-mers per GPU")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the baseline sample")
+    return ap.parse_args()
+
+
+def workload_name(n_gpus):
+    return (f"BASELINE configs[1]: synthetic diploid k={K} FastK table, het={HET:.0%}, cov={COV:g}x, L={LCUT}, "
+            f"~2e8 k-mers per GPU x {n_gpus} GPU(s)")
+
+
+# ------------------------------------------------------------------------------ clocks ------
+
+class ClockSampler:
+    """SM clock + throttle reasons during the timed region (pynvml; B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0, period=0.05):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        self.index, self.period = index, period
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80, "sync_boost": 0x10}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ---------------------------------------------------------------------- reference arm -------
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def scratch_dir():
+    for d in ("/dev/shm", tempfile.gettempdir()):
+        if os.path.isdir(d) and os.access(d, os.W_OK):
+            return tempfile.mkdtemp(prefix="hetmers_bench_", dir=d)
+    return tempfile.mkdtemp(prefix="hetmers_bench_")
+
+
+def make_sample_table(dirname, n_target, device):
+    """seeded table of ~n_target k-mers with the bench workload's parameters, written as FastK files"""
+    from tools import synth
+    G = synth.calibrate_G(K, int(n_target), PLOIDY, HET, COV, LCUT)
+    keys, cnt = synth.synth_table(K, G, PLOIDY, HET, COV, LCUT, SEED, device=device)
+    name = os.path.join(dirname, "sample")
+    synth.write_table(name, K, keys, cnt, ibyte=3, nparts=4)
+    return name, int(keys.numel())
+
+
+def time_reference(table, nels, threads, runs=1):
+    """wall clock of the CPU implementation on `table`; -> (seconds list, kind)"""
+    ref = os.path.join(ROOT, "oracle", "_ref", "hetmers")
+    ora = os.path.join(ROOT, "oracle", "hetmers_oracle")
+    out = os.path.join(os.path.dirname(table), "cpu_out")
+    times = []
+    for _ in range(runs):
+        if os.path.exists(out + ".smu"):
+            os.remove(out + ".smu")
+        if os.path.exists(ref):
+            cmd, kind = [ref, f"-e{LCUT}", f"-T{threads}", f"-o{out}", table], "reference"
+        else:
+            cmd, kind = [ora, f"-e{LCUT}", f"-o{out}", table], "port"
+        t0 = time.perf_counter()
+        r = subprocess.run(cmd, input="n\n", capture_output=True, text=True)
+        times.append(time.perf_counter() - t0)
+        if r.returncode != 0:
+            raise RuntimeError(f"CPU baseline failed: {r.stderr[-500:]}")
+    return times, kind, out + ".smu"
+
+
+def cpu_sample_size(args, threads):
+    # survey anchor: ~0.45e6 k-mers/s per thread at k=31; bounded by the GPU workload
+    n = 0.45e6 * threads * args.cpu_seconds
+    return int(max(2e6, min(n, args.nels)))
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    threads = min(host_cores(), 64)
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "hetmers")):
+        threads = 1
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    d = scratch_dir()
+    try:
+        n_s = cpu_sample_size(args, threads)
+        table, nels = make_sample_table(d, n_s, dev)
+        warm, kind, _ = time_reference(table, nels, threads, runs=max(args.warmup, 0))
+        secs, kind, _ = time_reference(table, nels, threads, runs=args.steps)
+        total = sum(secs)
+        value = nels * args.steps / total
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+                "data": "synthetic", "gpu_launches": 0,
+                "config": {"workload": workload_name(args.gpus), "k": K, "nels_sample": nels},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                                 "sample": f"one pass of the {'reference C hetmers' if kind == 'reference' else 'oracle port'} "
+                                           f"-T{threads} over a seeded {nels}-k-mer table of the same workload per step"},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+    finally:
+        import shutil
+        shutil.rmtree(d, ignore_errors=True)
+
+
+# -------------------------------------------------------------------------- our arm ---------
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def measured_traffic(nels):
+    """dram bytes per pass-1 launch from the committed ncu --set full capture, scaled per k-mer"""
+    p = os.path.join(ROOT, "profiles", "pass1_traffic.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            return float(j["dram_bytes_per_kmer"]) * nels
+        except Exception:
+            pass
+    return None
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hetmers path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    multi = world > 1
+    if multi:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from smudgeplot_b200 import _lib
+    from smudgeplot_b200.device import DeviceTable
+    from tools import synth
+    if multi:
+        from smudgeplot_b200 import dist as hdist
+
+    # ---- synthetic table (setup, untimed) ---------------------------------------------------
+    n_target = int(args.nels) * world
+    G = synth.calibrate_G(K, n_target, PLOIDY, HET, COV, LCUT)
+    if multi:
+        job = hdist.ShardedScan.from_synthetic(K, G, PLOIDY, HET, COV, LCUT, SEED, dev)
+        nels, my_n = job.n_total, job.hi - job.lo
+    else:
+        keys, cnt = synth.synth_table(K, G, PLOIDY, HET, COV, LCUT, SEED, device=dev)
+        table = DeviceTable(K, keys, cnt.to(torch.int16)).build_index()
+        table.alloc_work()
+        nels = my_n = table.n
+    torch.cuda.synchronize()
+
+    def one_scan(events=None):
+        if multi:
+            return job.scan(events)
+        table.deg.zero_()
+        table.plot.zero_()
+        if events is not None:
+            events[0].record()
+        table.pass1()
+        if events is not None:
+            events[1].record()
+        table.pass2()
+        return table.plot
+
+    for _ in range(max(args.warmup, 3)):
+        one_scan()
+    torch.cuda.synchronize()
+    if multi:
+        dist.barrier()
+    # ---- timed region: exactly K steps ------------------------------------------------------
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p1 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local) as clk:
+        torch.cuda.synchronize()
+        ev0.record()
+        for s in range(args.steps):
+            plot = one_scan(p1[s])
+        ev1.record()
+        torch.cuda.synchronize()
+        if multi:
+            dist.barrier()
+        ms_total = ev0.elapsed_time(ev1)
+        ms_p1 = sum(a.elapsed_time(b) for a, b in p1) / args.steps
+        # keep the sampler alive over the e2e region too (more samples under load)
+        e2e = None
+        if not args.no_e2e:
+            e2e = measure_e2e(args, torch, dist, dev, multi, world, rank,
+                              job if multi else None, (keys, cnt) if not multi else None)
+    if multi:
+        t = torch.tensor([ms_total, ms_p1], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_p1 = t.tolist()
+    ms_step = ms_total / args.steps
+    value = nels / (ms_step * 1e-3)
+    launches = (3 if multi else 2) * args.steps
+
+    peak, peak_src = peaks()
+    per_launch = nels / world
+    achieved = ALGO_BYTES_PER_KMER * per_launch / (ms_p1 * 1e-3) / 1e9
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_name(world), "k": K, "ploidy": PLOIDY, "het": HET, "cov": COV, "L": LCUT,
+                       "nels": nels, "nels_per_gpu": my_n, "seed": SEED, "bucket_bits": (job.bits if multi else table.bits),
+                       "parallelism": f"table replica per GPU, {world} contiguous index shards" if multi else "1 GPU",
+                       "l2": "inputs (>=1.9 GB table + bucket index per GPU) exceed the 126 MB L2; no flush between iterations"},
+            "clocks": clk.summary(), "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "pass1_degree_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                         "algorithmic_bytes_per_kmer": ALGO_BYTES_PER_KMER, "ms_per_launch": ms_p1,
+                         "traffic": measured_traffic(per_launch)}}
+    if e2e is not None:
+        line["e2e"] = e2e
+    if rank == 0:
+        if not args.no_cpu and world == 1:
+            line["cpu_baseline"] = cpu_baseline(args, dev)
+        print(json.dumps(line), flush=True)
+    if multi:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, dev):
+    threads = min(host_cores(), 64)
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "hetmers")):
+        threads = 1
+    d = scratch_dir()
+    try:
+        n_s = cpu_sample_size(args, threads)
+        table, nels = make_sample_table(d, n_s, dev)
+        secs, kind, smu = time_reference(table, nels, threads, runs=1)
+        # parity while we are here: our executable on the same files must write the same .smu
+        from smudgeplot_b200 import hetmers
+        out = os.path.join(d, "gpu_out")
+        t0 = time.perf_counter()
+        hetmers.run_hetmers(table, o=out, L=LCUT, t=threads)
+        t_gpu = time.perf_counter() - t0
+        same = open(out + ".smu").read() == open(smu).read()
+        return {"value": nels / secs[0], "unit": UNIT, "cores": threads, "kind": kind,
+                "sample": f"one run of {'oracle/_ref/hetmers (unmodified reference C)' if kind == 'reference' else 'the oracle port'} "
+                          f"-e{LCUT} -T{threads} on a seeded {nels}-k-mer table of the same workload (4 part files in "
+                          f"{os.path.dirname(table)}, warm page cache), wall clock {secs[0]:.2f} s",
+                "seconds": secs[0], "nels": nels,
+                "our_executable_same_files": {"seconds_wall": t_gpu, "smu_identical": same}}
+    finally:
+        import shutil
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def measure_e2e(args, torch, dist, dev, multi, world, rank, job, tabl):
+    """the same scan through the public host-buffer API, copies inside the timed region"""
+    import ctypes as C
+    from smudgeplot_b200 import _lib
+    if multi:
+        return job.measure_e2e(args.steps, max(args.warmup, 1))
+    keys, cnt = tabl
+    n = keys.numel()
+    kbyte, ibyte = (K + 3) // 4, 3
+    pbyte = kbyte - ibyte + 2
+    # FastK records + stub index built on the GPU (setup), then parked in pinned host memory
+    rec = torch.empty((n, pbyte), dtype=torch.uint8, device=dev)
+    for j in range(ibyte, kbyte):
+        rec[:, j - ibyte] = ((keys >> (56 - 8 * j)) & 0xFF).to(torch.uint8)
+    rec[:, pbyte - 2] = (cnt & 0xFF).to(torch.uint8)
+    rec[:, pbyte - 1] = ((cnt >> 8) & 0xFF).to(torch.uint8)
+    pre = (keys >> 40) & 0xFFFFFF
+    index = torch.cumsum(torch.bincount(pre, minlength=1 << 24), 0)
+    h_rec = torch.empty(rec.numel(), dtype=torch.uint8, pin_memory=True)
+    h_rec.copy_(rec.view(-1))
+    h_idx = torch.empty(1 << 24, dtype=torch.int64, pin_memory=True)
+    h_idx.copy_(index)
+    del rec, pre, index
+    torch.cuda.synchronize()
+    L = _lib.lib()
+    part_nels = (C.c_int64 * 1)(n)
+    part_rec = (C.c_void_p * 1)(h_rec.data_ptr())
+    ht = _lib.HostTable(K, ibyte, 1, LCUT, n, C.cast(h_idx.data_ptr(), C.POINTER(C.c_int64)), part_nels, part_rec)
+    devs = (C.c_int * 1)(dev.index or 0)
+    plot = torch.empty(_lib.PLOT_CELLS, dtype=torch.int64, pin_memory=True)
+    st = _lib.ScanStats()
+
+    def call():
+        _lib.check(L.hm_hetmers_host(C.byref(ht), devs, 1, plot.data_ptr(), C.byref(st)))
+
+    for _ in range(max(args.warmup, 1)):
+        call()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        call()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / args.steps
+    return {"value": n / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
+            "h2d_bytes_per_step": int(h_rec.numel() + h_idx.numel() * 8),
+            "d2h_bytes_per_step": int(_lib.PLOT_CELLS * 8),
+            "api": "hm_hetmers_host(hm_host_table in pinned host memory) -> int64 plot[1001*501]",
+            "last_call_ms": {"load": st.ms_h2d_unpack, "pass1": st.ms_pass1, "pass2": st.ms_pass2},
+            "kernel_launches_per_call": int(st.kernel_launches)}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

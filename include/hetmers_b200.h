@@ -1,0 +1,163 @@
+/*******************************************************************************************
+ * hetmers_b200.h -- C ABI of libhetmers_b200.so, the B200 (sm_100a) implementation of
+ * smudgeplot's `hetmers` hot path.
+ *
+ * The reference has NO in-process API for this path: its boundary is the `hetmers` executable
+ * spawned by smudgeplot's CLI (/root/reference/src/smudgeplot/cli.py:57-72,348-361) and the
+ * whole computation lives in src/lib/PloidyPlot.c + the Kmer_Stream part of src/lib/libfastk.c.
+ * The drop-in therefore is our own `hetmers` executable (smudgeplot_b200/host/hetmers_main.c,
+ * plain C); this header is the thin layer between that C host (or any FFI: ctypes, cgo, JNI)
+ * and the CUDA kernels.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Every entry point names the reference code it replaces (file:line under /root/reference).
+ * All functions return 0 on success and a negative HM_E* code on failure; hm_last_error()
+ * gives the message (thread-local).  There is NO CPU fallback anywhere behind this ABI.
+ *
+ * Layers
+ *   A. hm_k_*      kernels on caller-owned DEVICE memory, enqueued on a caller stream
+ *                  (used by the torch.distributed plumbing in smudgeplot_b200/dist.py and by B)
+ *   B. hm_scan_*   whole path from HOST buffers holding raw FastK part payloads: H2D, unpack,
+ *                  bucket index, pass 1, pass 2, D2H of the plot (used by hetmers_main.c,
+ *                  by smudgeplot_b200.hetmers() and by bench.py's e2e leg)
+ *   C. hm_table_*  FastK stub/part parser on the host (plain C, host/fastk_table.c)
+ *******************************************************************************************/
+#ifndef HETMERS_B200_H
+#define HETMERS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HM_SMAX        1000                 /* max CovA+CovB      (PloidyPlot.c:48) */
+#define HM_FMAX         500                 /* max min(CovA,CovB) (PloidyPlot.c:49) */
+#define HM_PLOT_W      (HM_FMAX+1)
+#define HM_PLOT_CELLS  ((HM_SMAX+1)*(HM_FMAX+1))   /* int64 plot[1001][501] (PloidyPlot.c:1466-1473) */
+#define HM_MAX_KMER      32                 /* one 64-bit word per packed k-mer (this round) */
+
+#define HM_OK            0
+#define HM_EINVAL       -1                  /* bad argument                                   */
+#define HM_ECUDA        -2                  /* CUDA runtime / launch failure                  */
+#define HM_ENOMEM       -3                  /* host or device allocation failed               */
+#define HM_EIO          -4                  /* cannot open / read a table file                */
+#define HM_EFORMAT      -5                  /* malformed FastK table                          */
+#define HM_EUNSUPPORTED -6                  /* valid input this build does not handle (k>32)  */
+
+const char *hm_last_error(void);
+int         hm_abi_version(void);
+/* number of visible CUDA devices (0 if none / no driver) */
+int         hm_device_count(void);
+/* name, SM count and total memory of device `dev` (for -v / bench provenance) */
+int         hm_device_info(int dev, char *name, int name_len, int *sm_count, int64_t *total_mem);
+
+/* ======================= A. kernels on device memory ===================================== *
+ * Device table layout (structure of arrays):
+ *   keys  uint64[n]  packed 2-bit k-mer, LEFT aligned (base i in bits 63-2i..62-2i), ascending;
+ *                    uint64 order == FastK table order (libfastk.c packing :571-579)
+ *   cnt   uint16[n]  k-mer counts
+ *   deg   uint8 [n]  incidence array == the reference's `Pair` (PloidyPlot.c:163), allocated
+ *                    with size rounded up to a multiple of 4 and 4-byte aligned
+ *   bucket           lower-bound offsets of every `bits`-bit key prefix, (1<<bits)+1 entries,
+ *                    uint32 if idx64==0 (n < 2^32-1) else uint64
+ * `stream` is a cudaStream_t passed as void* (NULL = default stream).                        */
+
+/* FastK part records -> SoA.  Replaces Next_Kmer_Entry/Current_Entry (libfastk.c:1159-1176,
+ * :1230-1269): re-attaches the ibyte-byte prefix found from the stub index and splits the
+ * unaligned (suffix || uint16 count) record.  d_rec: n records of pbyte=kbyte-ibyte+2 bytes,
+ * holding table ordinals [first, first+n); d_stub_index: int64[1<<(8*ibyte)] on the device.   */
+int hm_k_unpack_records(const uint8_t *d_rec, int64_t n, int64_t first,
+                        const int64_t *d_stub_index, int ibyte, int kmer,
+                        uint64_t *d_keys, uint16_t *d_cnt, void *stream);
+
+/* Prefix (bucket) index over the sorted keys; takes the place of the stub index + on-disk
+ * bisection of GoTo_Kmer_Entry (libfastk.c:1320-1409).                                        */
+int hm_k_build_bucket_index(const uint64_t *d_keys, int64_t n, int bits,
+                            void *d_bucket, int idx64, void *stream);
+
+/* Pass 1 (PASS1=1 of PloidyPlot.c:1489; analysis_in_core_1 :454-568, analysis_thread_1
+ * :168-301, big_window :712-842): for every entry x in [lo,hi) find every one-substitution
+ * neighbour y > x in the table; for each such pair with cnt sum <= SMAX add 1 to deg[x] and
+ * deg[y] (mod 256, atomically) and remember the pair's upper member in d_up[x-lo]
+ * (all-ones = none).  d_deg must be zeroed by the caller before the first call.              */
+int hm_k_pass1_degree(const uint64_t *d_keys, const uint16_t *d_cnt, int64_t n,
+                      const void *d_bucket, int bits, int idx64, int kmer,
+                      int64_t lo, int64_t hi, uint8_t *d_deg, void *d_up, void *stream);
+
+/* Pass 2 (PASS1=0; analysis_in_core_2 :570-700, analysis_thread_2 :303-452): for x in [lo,hi)
+ * with deg[x]<=1 whose recorded upper partner y has deg[y]<=1: plot[cx+cy][min(cx,cy)] += 1.
+ * d_plot: uint64[HM_PLOT_CELLS], accumulated into (caller zeroes it).                        */
+int hm_k_pass2_plot(const uint16_t *d_cnt, const uint8_t *d_deg, const void *d_up, int idx64,
+                    int64_t lo, int64_t hi, unsigned long long *d_plot, void *stream);
+
+/* examine_table (PloidyPlot.c:1167-1197): smallest count v>=1 (read as int16) in [frst,last);
+ * *d_min (device int) must be preset to 0x8000.                                               */
+int hm_k_min_count(const uint16_t *d_cnt, int64_t frst, int64_t last, int *d_min, void *stream);
+
+/* exact-match lookup of nq packed k-mers: d_pos[q] = table index or -1.  Replaces
+ * GoTo_Kmer_Entry's "return 1 iff exact hit" use (libfastk.c:1320-1409; PloidyPlot.c:1213). */
+int hm_k_find_keys(const uint64_t *d_keys, int64_t n, const void *d_bucket, int bits, int idx64,
+                   const uint64_t *d_query, int64_t nq, int64_t *d_pos, void *stream);
+
+/* choice of bucket-index width for a table of n entries */
+int hm_pick_bucket_bits(int64_t n);
+
+/* ======================= B. whole path from host buffers ================================= */
+
+typedef struct hm_host_table
+  { int32_t         kmer;        /* k                                                   */
+    int32_t         ibyte;       /* prefix bytes folded into the stub index (1..3)      */
+    int32_t         nparts;
+    int32_t         minval;
+    int64_t         nels;        /* sum of part_nels                                    */
+    const int64_t  *index;       /* int64[1 << (8*ibyte)] bucket END offsets            */
+    const int64_t  *part_nels;   /* [nparts]                                            */
+    const uint8_t **part_rec;    /* [nparts] payloads: part_nels[p]*pbyte bytes each    */
+  } hm_host_table;
+
+typedef struct hm_scan_stats
+  { int64_t nels;
+    int32_t n_gpus;
+    int32_t bucket_bits;
+    double  ms_h2d_unpack;       /* H2D copies + unpack + bucket index (T_load, device part) */
+    double  ms_pass1;
+    double  ms_pass2;
+    double  ms_scan;             /* pass1 + exchange + pass2 + plot reduce (T_scan)          */
+    double  ms_total;            /* wall clock of the call                                   */
+    int64_t kernel_launches;     /* kernels of ours launched by the call                     */
+  } hm_scan_stats;
+
+typedef struct hm_scan hm_scan;   /* opaque: device-resident table + work buffers            */
+
+/* Load a table onto `n_gpus` devices (ids dev[0..n_gpus-1]; every device holds a full replica,
+ * work is sharded by contiguous index range).  Replaces Open_Kmer_Stream +
+ * Clone_Kmer_Stream + the 4 GiB cache fill (libfastk.c:786-951; PloidyPlot.c:954-964).       */
+int  hm_scan_create(const hm_host_table *t, const int *dev, int n_gpus, hm_scan **out);
+void hm_scan_destroy(hm_scan *s);
+/* examine_table decisions (PloidyPlot.c:1167-1230) computed on the device */
+int  hm_scan_examine(hm_scan *s, int ethresh, int *trim, int *symm);
+/* both passes; plot: host int64[HM_PLOT_CELLS]; stats optional */
+int  hm_scan_run(hm_scan *s, int64_t *plot, hm_scan_stats *stats);
+/* one call: create + run + destroy (what bench.py's e2e leg times) */
+int  hm_hetmers_host(const hm_host_table *t, const int *dev, int n_gpus,
+                     int64_t *plot, hm_scan_stats *stats);
+/* copy device arrays back for tests: any pointer may be NULL */
+int  hm_scan_download(hm_scan *s, uint64_t *keys, uint16_t *cnt, uint8_t *deg);
+
+/* ======================= C. FastK table files (host, plain C) ============================ */
+
+typedef struct hm_table hm_table;          /* parsed stub + mapped part payloads            */
+
+/* Open <name>[.ktab] + hidden parts; replaces Open_Kmer_Stream (libfastk.c:786-908).
+ * HM_EIO if the stub cannot be opened (the reference's "Cannot open k-mer table").          */
+int  hm_table_open(const char *name, hm_table **out);
+void hm_table_close(hm_table *t);
+const hm_host_table *hm_table_view(const hm_table *t);
+
+/* .smu writer: "min\t(sum-min)\tcount\n", sum-major, min < FMAX (PloidyPlot.c:1603-1617) */
+int  hm_write_smu(const char *path, const int64_t *plot);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,395 @@
+/*******************************************************************************************
+ * hm_scan.cu -- layer B of include/hetmers_b200.h: the whole hetmers path from HOST buffers.
+ *
+ *   hm_scan_create   H2D of the raw FastK part payloads (double-buffered, copy stream ||
+ *                    unpack stream), SoA unpack, bucket index          ("T_load", device part)
+ *   hm_scan_examine  trimmed? / symmetric? decisions of examine_table (PloidyPlot.c:1167-1230)
+ *   hm_scan_run      pass 1 -> (degree exchange when >1 GPU) -> pass 2 -> plot D2H  ("T_scan")
+ *
+ * Every device holds a full replica of the table (180 GB HBM3e holds 16e9 k=31 entries); work is
+ * sharded by contiguous index range [lo_g, hi_g).  With one GPU there is no exchange at all.
+ * With several GPUs in this single process the loader gathers the shards over NVLink peer
+ * copies and the degree bytes are summed by a peer-memory kernel (hm_peer.cu); the
+ * one-process-per-GPU variant (torch.distributed / NCCL) lives in smudgeplot_b200/dist.py and
+ * uses layer A directly.
+ *******************************************************************************************/
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "hetmers_b200.h"
+#include "hm_internal.h"
+
+#define HM_MAX_GPUS 16
+#define LOAD_CHUNK  (16ll<<20)        /* records per H2D/unpack chunk */
+
+typedef struct
+  { int                 dev;
+    cudaStream_t        st, st_copy;
+    uint64_t           *keys;
+    uint16_t           *cnt;
+    uint8_t            *deg;          /* n rounded up to 4 */
+    void               *bucket;
+    void               *up;           /* hi-lo entries */
+    unsigned long long *plot;
+    int64_t             lo, hi;       /* this device's work range */
+  } DevTable;
+
+struct hm_scan
+  { int      kmer, ibyte, bits, idx64, ngpu;
+    int64_t  n;
+    DevTable d[HM_MAX_GPUS];
+    double   ms_load;
+    int64_t  launches;
+  };
+
+static double now_ms(void)
+{ struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC,&ts);
+  return ts.tv_sec*1e3 + ts.tv_nsec*1e-6;
+}
+
+/* multi-GPU helpers (hm_peer.cu) */
+int hm_peer_enable(const int *dev, int n);
+int hm_peer_sum_deg(uint8_t **deg, const int64_t *lo, const int64_t *hi, const int *dev,
+                    cudaStream_t *st, int n, int64_t nels);
+int hm_peer_sum_plot(unsigned long long **plot, const int *dev, cudaStream_t *st, int n);
+
+static void free_dev(DevTable *D)
+{ cudaSetDevice(D->dev);
+  if (D->keys)   cudaFree(D->keys);
+  if (D->cnt)    cudaFree(D->cnt);
+  if (D->deg)    cudaFree(D->deg);
+  if (D->bucket) cudaFree(D->bucket);
+  if (D->up)     cudaFree(D->up);
+  if (D->plot)   cudaFree(D->plot);
+  if (D->st)      cudaStreamDestroy(D->st);
+  if (D->st_copy) cudaStreamDestroy(D->st_copy);
+  memset(D,0,sizeof(*D));
+}
+
+extern "C" void hm_scan_destroy(hm_scan *s)
+{ if (s == NULL)
+    return;
+  for (int g = 0; g < s->ngpu; g++)
+    free_dev(s->d+g);
+  free(s);
+}
+
+/* Load ordinals [first, first+count) of the table onto device D (keys/cnt already allocated for
+ * the full table).  Walks the parts, copies payload chunks H2D on st_copy into one of two staging
+ * buffers and unpacks them on st.                                                              */
+static int load_range(hm_scan *s, DevTable *D, const hm_host_table *t, const int64_t *d_index,
+                      int64_t first, int64_t count)
+{ int      kbyte = (t->kmer+3)>>2;
+  int      pbyte = kbyte - t->ibyte + 2;
+  uint8_t *stage[2] = { NULL, NULL };
+  cudaEvent_t copied[2], unpacked[2];
+  int64_t  chunk = LOAD_CHUNK;
+  int      rc = HM_OK, b = 0, used[2] = {0,0};
+
+  if (count <= 0)
+    return HM_OK;
+  if (chunk > count) chunk = count;
+  for (int i = 0; i < 2; i++)
+    { HM_CUDA(cudaMalloc(&stage[i],(size_t) chunk*pbyte));
+      HM_CUDA(cudaEventCreateWithFlags(&copied[i],cudaEventDisableTiming));
+      HM_CUDA(cudaEventCreateWithFlags(&unpacked[i],cudaEventDisableTiming));
+    }
+  int64_t pstart = 0;                               /* ordinal of the part's first record */
+  for (int p = 0; p < t->nparts && rc == HM_OK; p++)
+    { int64_t pn   = t->part_nels[p];
+      int64_t from = first > pstart ? first : pstart;
+      int64_t to   = first+count < pstart+pn ? first+count : pstart+pn;
+      for (int64_t o = from; o < to && rc == HM_OK; o += chunk)
+        { int64_t m = to-o < chunk ? to-o : chunk;
+          if (used[b])
+            cudaStreamWaitEvent(D->st_copy,unpacked[b],0);
+          cudaError_t e = cudaMemcpyAsync(stage[b],t->part_rec[p] + (o-pstart)*pbyte,
+                                          (size_t) m*pbyte,cudaMemcpyHostToDevice,D->st_copy);
+          if (e != cudaSuccess) { rc = hm_cuda_fail(e,"cudaMemcpyAsync(H2D records)"); break; }
+          cudaEventRecord(copied[b],D->st_copy);
+          cudaStreamWaitEvent(D->st,copied[b],0);
+          rc = hm_k_unpack_records(stage[b],m,o,d_index,t->ibyte,t->kmer,D->keys+o,D->cnt+o,D->st);
+          s->launches += 1;
+          cudaEventRecord(unpacked[b],D->st);
+          used[b] = 1;
+          b ^= 1;
+        }
+      pstart += pn;
+    }
+  cudaStreamSynchronize(D->st_copy);
+  cudaError_t e = cudaStreamSynchronize(D->st);
+  for (int i = 0; i < 2; i++)
+    { cudaFree(stage[i]); cudaEventDestroy(copied[i]); cudaEventDestroy(unpacked[i]); }
+  if (rc == HM_OK && e != cudaSuccess)
+    rc = hm_cuda_fail(e,"unpack");
+  return rc;
+}
+
+extern "C" int hm_scan_create(const hm_host_table *t, const int *dev, int n_gpus, hm_scan **out)
+{ double t0 = now_ms();
+  if (t == NULL || out == NULL || n_gpus < 1 || n_gpus > HM_MAX_GPUS)
+    return hm_set_error(HM_EINVAL,"hm_scan_create: bad arguments");
+  if (t->kmer < 1 || t->kmer > HM_MAX_KMER)
+    return hm_set_error(HM_EUNSUPPORTED,"k-mer length %d not supported by this build (1..%d)",
+                        t->kmer,HM_MAX_KMER);
+  int kbyte = (t->kmer+3)>>2;
+  if (t->ibyte < 1 || t->ibyte > 3 || t->ibyte > kbyte)
+    return hm_set_error(HM_EFORMAT,"table has ibyte=%d with k=%d",t->ibyte,t->kmer);
+  if (hm_device_count() < 1)
+    return hm_set_error(HM_ECUDA,"no CUDA device visible (this build has no CPU fallback)");
+
+  hm_scan *s = (hm_scan *) calloc(1,sizeof(hm_scan));
+  if (s == NULL)
+    return hm_set_error(HM_ENOMEM,"out of host memory");
+  s->kmer = t->kmer; s->ibyte = t->ibyte; s->n = t->nels; s->ngpu = n_gpus;
+  s->bits  = hm_pick_bucket_bits(s->n);
+  s->idx64 = (s->n >= 0xFFFFFFF0ll);
+  int64_t n  = s->n;
+  size_t  ib = s->idx64 ? 8 : 4;
+  int64_t ixlen = (int64_t) 1 << (8*t->ibyte);
+  int     rc = HM_OK;
+
+  if (n_gpus > 1 && (rc = hm_peer_enable(dev,n_gpus)) != HM_OK)
+    { free(s); return rc; }
+
+  for (int g = 0; g < n_gpus && rc == HM_OK; g++)
+    { DevTable *D = s->d+g;
+      D->dev = dev ? dev[g] : g;
+      D->lo  = n*g/n_gpus;
+      D->hi  = n*(g+1)/n_gpus;
+      cudaError_t e;
+#define TRY(call) if (rc == HM_OK && (e = (call)) != cudaSuccess) rc = hm_cuda_fail(e,#call)
+      TRY(cudaSetDevice(D->dev));
+      TRY(cudaStreamCreateWithFlags(&D->st,cudaStreamNonBlocking));
+      TRY(cudaStreamCreateWithFlags(&D->st_copy,cudaStreamNonBlocking));
+      TRY(cudaMalloc(&D->keys,sizeof(uint64_t)*(size_t) (n+1)));
+      TRY(cudaMalloc(&D->cnt,sizeof(uint16_t)*(size_t) (n+1)));
+      TRY(cudaMalloc(&D->deg,(size_t) ((n+4)&~3ll)));
+      TRY(cudaMalloc(&D->bucket,ib*(((size_t) 1<<s->bits)+1)));
+      TRY(cudaMalloc(&D->up,ib*(size_t) (D->hi-D->lo+1)));
+      TRY(cudaMalloc(&D->plot,sizeof(unsigned long long)*HM_PLOT_CELLS));
+#undef TRY
+    }
+
+  /* each device unpacks its own shard from the host, then the shards are exchanged over peer
+   * copies so that every device ends with the full table                                      */
+  for (int g = 0; g < n_gpus && rc == HM_OK; g++)
+    { DevTable *D = s->d+g;
+      int64_t  *d_index = NULL;
+      cudaSetDevice(D->dev);
+      cudaError_t e = cudaMalloc(&d_index,sizeof(int64_t)*ixlen);
+      if (e != cudaSuccess) { rc = hm_cuda_fail(e,"cudaMalloc(stub index)"); break; }
+      e = cudaMemcpyAsync(d_index,t->index,sizeof(int64_t)*ixlen,cudaMemcpyHostToDevice,D->st);
+      if (e != cudaSuccess) { rc = hm_cuda_fail(e,"cudaMemcpyAsync(stub index)"); cudaFree(d_index); break; }
+      rc = load_range(s,D,t,d_index,D->lo,D->hi-D->lo);
+      cudaFree(d_index);
+    }
+  if (n_gpus > 1 && rc == HM_OK)
+    { for (int g = 0; g < n_gpus && rc == HM_OK; g++)        /* all-gather by peer copies */
+        for (int h = 0; h < n_gpus && rc == HM_OK; h++)
+          if (h != g)
+            { DevTable *S = s->d+h, *D = s->d+g;
+              int64_t m = S->hi-S->lo;
+              if (m <= 0) continue;
+              cudaSetDevice(D->dev);
+              cudaError_t e = cudaMemcpyPeerAsync(D->keys+S->lo,D->dev,S->keys+S->lo,S->dev,
+                                                  sizeof(uint64_t)*(size_t) m,D->st);
+              if (e == cudaSuccess)
+                e = cudaMemcpyPeerAsync(D->cnt+S->lo,D->dev,S->cnt+S->lo,S->dev,
+                                        sizeof(uint16_t)*(size_t) m,D->st);
+              if (e != cudaSuccess) rc = hm_cuda_fail(e,"cudaMemcpyPeerAsync(table shard)");
+            }
+      for (int g = 0; g < n_gpus; g++)
+        { cudaSetDevice(s->d[g].dev); cudaStreamSynchronize(s->d[g].st); }
+    }
+  for (int g = 0; g < n_gpus && rc == HM_OK; g++)
+    { DevTable *D = s->d+g;
+      cudaSetDevice(D->dev);
+      rc = hm_k_build_bucket_index(D->keys,n,s->bits,D->bucket,s->idx64,D->st);
+      s->launches += 1;
+    }
+  for (int g = 0; g < n_gpus; g++)
+    { cudaSetDevice(s->d[g].dev);
+      cudaError_t e = cudaStreamSynchronize(s->d[g].st);
+      if (rc == HM_OK && e != cudaSuccess) rc = hm_cuda_fail(e,"table load");
+    }
+  if (rc != HM_OK)
+    { hm_scan_destroy(s); return rc; }
+  s->ms_load = now_ms()-t0;
+  *out = s;
+  return HM_OK;
+}
+
+/* reverse complement of a left-aligned packed k-mer (k <= 32) */
+static uint64_t revcomp64(uint64_t x, int k)
+{ x = ~x;
+  x = ((x >> 2)  & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+  x = ((x >> 4)  & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+  x = ((x >> 8)  & 0x00FF00FF00FF00FFull) | ((x & 0x00FF00FF00FF00FFull) << 8);
+  x = ((x >> 16) & 0x0000FFFF0000FFFFull) | ((x & 0x0000FFFF0000FFFFull) << 16);
+  x = (x >> 32) | (x << 32);
+  if (k < 32)
+    x = (x & (((uint64_t) 1 << (2*k))-1)) << (64-2*k);
+  return x;
+}
+
+/* examine_table (PloidyPlot.c:1167-1230).  trim: smallest non-zero count among the middle <=1e8
+ * entries >= ethresh.  symm: reverse complement of entry 1 (moving on past palindromes, where
+ * the reference's loop would never terminate) is present.                                      */
+extern "C" int hm_scan_examine(hm_scan *s, int ethresh, int *trim, int *symm)
+{ DevTable *D = s->d;
+  int64_t   n = s->n, frst, last;
+  int       h_min = 0x8000, *d_min = NULL;
+  uint64_t *d_q = NULL;
+  int64_t  *d_pos = NULL;
+
+  HM_CUDA(cudaSetDevice(D->dev));
+  if (n+3 < 100000000) { frst = 0; last = n; }
+  else { frst = n/2-50000000; last = n/2+50000000; }
+  HM_CUDA(cudaMalloc(&d_min,sizeof(int)));
+  HM_CUDA(cudaMemcpyAsync(d_min,&h_min,sizeof(int),cudaMemcpyHostToDevice,D->st));
+  int rc = hm_k_min_count(D->cnt,frst,last,d_min,D->st);
+  s->launches += 1;
+  if (rc == HM_OK)
+    { cudaError_t e = cudaMemcpyAsync(&h_min,d_min,sizeof(int),cudaMemcpyDeviceToHost,D->st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(D->st);
+      if (e != cudaSuccess) rc = hm_cuda_fail(e,"min_count");
+    }
+  cudaFree(d_min);
+  if (rc != HM_OK)
+    return rc;
+  *trim = (h_min >= ethresh);
+
+  *symm = 1;
+  HM_CUDA(cudaMalloc(&d_q,sizeof(uint64_t)));
+  HM_CUDA(cudaMalloc(&d_pos,sizeof(int64_t)));
+  for (int64_t sidx = 1; sidx < n; sidx++)
+    { uint64_t x, q;
+      int64_t  pos;
+      cudaError_t e = cudaMemcpyAsync(&x,D->keys+sidx,sizeof(uint64_t),cudaMemcpyDeviceToHost,D->st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(D->st);
+      if (e != cudaSuccess) { rc = hm_cuda_fail(e,"examine: key fetch"); break; }
+      q = revcomp64(x,s->kmer);
+      cudaMemcpyAsync(d_q,&q,sizeof(uint64_t),cudaMemcpyHostToDevice,D->st);
+      rc = hm_k_find_keys(D->keys,n,D->bucket,s->bits,s->idx64,d_q,1,d_pos,D->st);
+      s->launches += 1;
+      if (rc != HM_OK) break;
+      e = cudaMemcpyAsync(&pos,d_pos,sizeof(int64_t),cudaMemcpyDeviceToHost,D->st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(D->st);
+      if (e != cudaSuccess) { rc = hm_cuda_fail(e,"examine: lookup"); break; }
+      if (pos < 0) { *symm = 0; break; }
+      if (pos != sidx) { *symm = 1; break; }
+    }
+  cudaFree(d_q); cudaFree(d_pos);
+  return rc;
+}
+
+extern "C" int hm_scan_run(hm_scan *s, int64_t *plot, hm_scan_stats *stats)
+{ double      t0 = now_ms();
+  int         G = s->ngpu, rc = HM_OK;
+  int64_t     n = s->n, launches0 = s->launches;
+  cudaEvent_t ev[HM_MAX_GPUS][4];
+  float       ms1 = 0, ms2 = 0, msall = 0;
+
+  for (int g = 0; g < G; g++)
+    { DevTable *D = s->d+g;
+      HM_CUDA(cudaSetDevice(D->dev));
+      for (int k = 0; k < 4; k++)
+        HM_CUDA(cudaEventCreate(&ev[g][k]));
+      HM_CUDA(cudaEventRecord(ev[g][0],D->st));
+      HM_CUDA(cudaMemsetAsync(D->deg,0,(size_t) ((n+4)&~3ll),D->st));
+      HM_CUDA(cudaMemsetAsync(D->plot,0,sizeof(unsigned long long)*HM_PLOT_CELLS,D->st));
+      rc = hm_k_pass1_degree(D->keys,D->cnt,n,D->bucket,s->bits,s->idx64,s->kmer,
+                             D->lo,D->hi,D->deg,D->up,D->st);
+      if (rc != HM_OK) return rc;
+      s->launches += (D->hi > D->lo);
+      HM_CUDA(cudaEventRecord(ev[g][1],D->st));
+    }
+  if (G > 1)
+    { uint8_t *deg[HM_MAX_GPUS]; int64_t lo[HM_MAX_GPUS], hi[HM_MAX_GPUS];
+      int dev[HM_MAX_GPUS]; cudaStream_t st[HM_MAX_GPUS];
+      for (int g = 0; g < G; g++)
+        { deg[g] = s->d[g].deg; lo[g] = s->d[g].lo; hi[g] = s->d[g].hi;
+          dev[g] = s->d[g].dev; st[g] = s->d[g].st;
+        }
+      rc = hm_peer_sum_deg(deg,lo,hi,dev,st,G,n);
+      if (rc != HM_OK) return rc;
+      s->launches += G;
+    }
+  for (int g = 0; g < G; g++)
+    { DevTable *D = s->d+g;
+      HM_CUDA(cudaSetDevice(D->dev));
+      HM_CUDA(cudaEventRecord(ev[g][2],D->st));
+      rc = hm_k_pass2_plot(D->cnt,D->deg,D->up,s->idx64,D->lo,D->hi,D->plot,D->st);
+      if (rc != HM_OK) return rc;
+      s->launches += (D->hi > D->lo);
+      HM_CUDA(cudaEventRecord(ev[g][3],D->st));
+    }
+  if (G > 1)
+    { unsigned long long *pl[HM_MAX_GPUS]; int dev[HM_MAX_GPUS]; cudaStream_t st[HM_MAX_GPUS];
+      for (int g = 0; g < G; g++)
+        { pl[g] = s->d[g].plot; dev[g] = s->d[g].dev; st[g] = s->d[g].st; }
+      rc = hm_peer_sum_plot(pl,dev,st,G);
+      if (rc != HM_OK) return rc;
+      s->launches += 1;
+    }
+  HM_CUDA(cudaSetDevice(s->d[0].dev));
+  HM_CUDA(cudaMemcpyAsync(plot,s->d[0].plot,sizeof(int64_t)*HM_PLOT_CELLS,
+                          cudaMemcpyDeviceToHost,s->d[0].st));
+  for (int g = 0; g < G; g++)
+    { HM_CUDA(cudaSetDevice(s->d[g].dev));
+      HM_CUDA(cudaStreamSynchronize(s->d[g].st));
+    }
+  double t1 = now_ms();
+  for (int g = 0; g < G; g++)
+    { float a = 0, b = 0, c = 0;
+      cudaSetDevice(s->d[g].dev);
+      cudaEventElapsedTime(&a,ev[g][0],ev[g][1]);
+      cudaEventElapsedTime(&b,ev[g][2],ev[g][3]);
+      cudaEventElapsedTime(&c,ev[g][0],ev[g][3]);
+      if (a > ms1) ms1 = a;
+      if (b > ms2) ms2 = b;
+      if (c > msall) msall = c;
+      for (int k = 0; k < 4; k++)
+        cudaEventDestroy(ev[g][k]);
+    }
+  if (stats != NULL)
+    { stats->nels = n; stats->n_gpus = G; stats->bucket_bits = s->bits;
+      stats->ms_h2d_unpack = s->ms_load;
+      stats->ms_pass1 = ms1; stats->ms_pass2 = ms2;
+      stats->ms_scan = G > 1 ? (t1-t0) : msall;
+      stats->ms_total = s->ms_load + (t1-t0);
+      stats->kernel_launches = s->launches;
+    }
+  (void) launches0;
+  return HM_OK;
+}
+
+extern "C" int hm_hetmers_host(const hm_host_table *t, const int *dev, int n_gpus,
+                               int64_t *plot, hm_scan_stats *stats)
+{ hm_scan *s = NULL;
+  int rc = hm_scan_create(t,dev,n_gpus,&s);
+  if (rc != HM_OK)
+    return rc;
+  rc = hm_scan_run(s,plot,stats);
+  hm_scan_destroy(s);
+  return rc;
+}
+
+extern "C" int hm_scan_download(hm_scan *s, uint64_t *keys, uint16_t *cnt, uint8_t *deg)
+{ DevTable *D = s->d;
+  HM_CUDA(cudaSetDevice(D->dev));
+  HM_CUDA(cudaStreamSynchronize(D->st));
+  if (keys != NULL)
+    HM_CUDA(cudaMemcpy(keys,D->keys,sizeof(uint64_t)*(size_t) s->n,cudaMemcpyDeviceToHost));
+  if (cnt != NULL)
+    HM_CUDA(cudaMemcpy(cnt,D->cnt,sizeof(uint16_t)*(size_t) s->n,cudaMemcpyDeviceToHost));
+  if (deg != NULL)
+    HM_CUDA(cudaMemcpy(deg,D->deg,(size_t) s->n,cudaMemcpyDeviceToHost));
+  return HM_OK;
+}

@@ -1,0 +1,321 @@
+/*******************************************************************************************
+ * hetmers_main.c -- the drop-in `hetmers` executable (plain C host; all compute is CUDA behind
+ * include/hetmers_b200.h).  Same process boundary as the reference binary that smudgeplot's CLI
+ * spawns (/root/reference/src/smudgeplot/cli.py:57-72,348-361):
+ *
+ *     hetmers [-v] [-T<int(4)>] [-P<dir(/tmp)>] [-o<output>] [-e<int(4)>] <source>[.ktab]
+ *
+ * mirrors main() of /root/reference/src/lib/PloidyPlot.c:1232-1630: argv grammar and messages
+ * (gene_core.h:32-56 ARG_* macros), default output root, the "Found het-table" prompt, the
+ * trimmed/symmetric examination and its shell-outs to FastK's Logex/Symmex/Fastrm, the verbose
+ * lines, the .smu format and the exit codes.  -T is accepted (and clamped to 64 with the same
+ * warning) but the GPU count comes from HETMERS_GPUS (default 1; "all" = every visible GPU).
+ * There is no CPU fallback: without a CUDA device the program fails with exit 1.
+ *******************************************************************************************/
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <strings.h>
+
+#include "hetmers_b200.h"
+
+static const char *Prog_Name = "hetmers";
+
+static const char *Usage[] = { " [-v] [-T<int(4)>] [-P<dir(/tmp)>]",
+                               " [-o<output>] [-e<int(4)>] <source>[.ktab]" };
+
+static int positive_arg(const char *arg, const char *what)      /* ARG_POSITIVE, gene_core.h:46-56 */
+{ char *eptr;
+  long  v = strtol(arg+2,&eptr,10);
+  if (*eptr != '\0' || arg[2] == '\0')
+    { fprintf(stderr,"%s: -%c '%s' argument is not an integer\n",Prog_Name,arg[1],arg+2);
+      exit (1);
+    }
+  if (v <= 0)
+    { fprintf(stderr,"%s: %s must be positive (%d)\n",Prog_Name,what,(int) v);
+      exit (1);
+    }
+  return ((int) v);
+}
+
+static void systemx(const char *command)                         /* SystemX, gene_core.c:19-24 */
+{ if (system(command) != 0)
+    { fprintf(stderr,"%s: Command '%s' failed\n",Prog_Name,command);
+      exit (1);
+    }
+}
+
+static void die_hm(void)
+{ fprintf(stderr,"%s: %s\n",Prog_Name,hm_last_error());
+  exit (1);
+}
+
+static int pick_gpus(int *devs)
+{ int ngpu = 1, navail = hm_device_count(), i;
+  const char *g = getenv("HETMERS_GPUS");
+
+  if (navail < 1)
+    { fprintf(stderr,"%s: no CUDA device is visible (this hetmers is GPU-only)\n",Prog_Name);
+      exit (1);
+    }
+  if (g != NULL && *g != '\0')
+    { if (strcasecmp(g,"all") == 0)
+        ngpu = navail;
+      else
+        ngpu = atoi(g);
+      if (ngpu < 1) ngpu = 1;
+      if (ngpu > navail)
+        { fprintf(stderr,"%s: Warning, only %d GPUs are visible\n",Prog_Name,navail);
+          ngpu = navail;
+        }
+    }
+  if (ngpu > 16) ngpu = 16;
+  for (i = 0; i < ngpu; i++)
+    devs[i] = i;
+  return (ngpu);
+}
+
+int main(int argc, char *argv[])
+{ int    VERBOSE = 0, NTHREADS = 4, ETHRESH = 4;
+  const char *SORT_PATH = "/tmp";
+  char  *OUT = NULL, *SRC;
+  const char *troot = "";      /* the reference's mktemp("._SPAIR.XXXX") fails on glibc and
+                                  leaves an empty root (PloidyPlot.c:1093,1313) */
+  int    i, j, k;
+  int    flags[128];
+
+  for (i = 0; i < 128; i++)
+    flags[i] = 0;
+
+  j = 1;
+  for (i = 1; i < argc; i++)
+    if (argv[i][0] == '-')
+      switch (argv[i][1])
+      { default:                                                  /* ARG_FLAGS("vklfs") */
+          for (k = 1; argv[i][k] != '\0'; k++)
+            { if (strchr("vklfs",argv[i][k]) == NULL)
+                { fprintf(stderr,"%s: -%c is an illegal option\n",Prog_Name,argv[i][k]);
+                  exit (1);
+                }
+              flags[(int) argv[i][k]] = 1;
+            }
+          break;
+        case 'e':
+          ETHRESH = positive_arg(argv[i],"Error-mer threshold");
+          break;
+        case 'o':
+          free(OUT);
+          OUT = strdup(argv[i]+2);
+          if (OUT == NULL)
+            exit (1);
+          break;
+        case 'P':
+          SORT_PATH = argv[i]+2;
+          break;
+        case 'T':
+          NTHREADS = positive_arg(argv[i],"Number of threads");
+          if (NTHREADS > 64)
+            { fprintf(stderr,"%s: Warning, only 64 threads will be used\n",Prog_Name);
+              NTHREADS = 64;
+            }
+          break;
+      }
+    else
+      argv[j++] = argv[i];
+  argc = j;
+
+  VERBOSE = flags['v'];
+
+  if (argc != 2)
+    { fprintf(stderr,"\nUsage: %s %s\n",Prog_Name,Usage[0]);
+      fprintf(stderr,"       %*s %s\n",(int) strlen(Prog_Name),"",Usage[1]);
+      fprintf(stderr,"\n");
+      fprintf(stderr,"      -o: root name for output table\n");
+      fprintf(stderr,"            default is root of <source> argument\n");
+      fprintf(stderr,"\n");
+      fprintf(stderr,"      -e: count threshold below which k-mers are considered erroneous\n");
+      fprintf(stderr,"      -v: verbose mode\n");
+      fprintf(stderr,"      -T: number of threads to use\n");
+      fprintf(stderr,"      -P: Place all temporary files in directory -P.\n");
+      exit (1);
+    }
+
+  SRC = argv[1];
+  if (OUT == NULL)                                   /* PathnRoot(src,".ktab"), gene_core.c:116-135 */
+    { size_t n = strlen(SRC);
+      OUT = strdup(SRC);
+      if (OUT == NULL)
+        exit (1);
+      if (n > 5 && strcasecmp(SRC+n-5,".ktab") == 0)
+        OUT[n-5] = '\0';
+    }
+
+  //  If appropriately named het-mer table found then ask if reuse (PloidyPlot.c:1318-1337)
+
+  { char *smu = malloc(strlen(OUT)+8);
+    FILE *f;
+    int   a;
+
+    sprintf(smu,"%s.smu",OUT);
+    f = fopen(smu,"r");
+    free(smu);
+    if (f != NULL)
+      { int bypass = 0;
+        fprintf(stdout,"\n  Found het-table %s.smu, use it? ",OUT);
+        fflush(stdout);
+        while ((a = getc(stdin)) != '\n')
+          { if (a == EOF)       /* the reference spins for ever here; we treat EOF as "no" */
+              break;
+            if (a == 'y' || a == 'Y')
+              bypass = 1;
+          }
+        if (bypass)
+          { fprintf(stderr,"\n  Using the found het-table, done\n");
+            fclose(f);
+            exit (0);
+          }
+        fclose(f);
+      }
+  }
+
+  //  Open input table and see if it needs conditioning (PloidyPlot.c:1341-1426)
+
+  hm_table *T;
+  hm_scan  *S;
+  char     *input = NULL;
+  int       ngpu, devs[16];
+
+  { char *command, *tname;
+    int   symm, trim;
+
+    tname   = malloc(strlen(SRC) + strlen(troot) + 10);
+    command = malloc(strlen(SRC) + strlen(troot) + strlen(SORT_PATH) + 100);
+    if (tname == NULL || command == NULL)
+      exit (1);
+
+    if (hm_table_open(SRC,&T) != HM_OK)
+      { if (strncmp(hm_last_error(),"Cannot open",11) == 0)
+          fprintf(stderr,"%s: Cannot open k-mer table %s\n",Prog_Name,SRC);
+        else
+          fprintf(stderr,"%s: %s\n",Prog_Name,hm_last_error());
+        exit (1);
+      }
+    ngpu = pick_gpus(devs);        /* after the table is known to exist: same first error as the reference */
+    if (hm_table_view(T)->nels < 2)
+      { fprintf(stderr,"%s: k-mer table %s has fewer than 2 entries\n",Prog_Name,SRC);
+        exit (1);
+      }
+    if (hm_scan_create(hm_table_view(T),devs,ngpu,&S) != HM_OK)
+      die_hm();
+    if (hm_scan_examine(S,ETHRESH,&trim,&symm) != HM_OK)
+      die_hm();
+
+    if (VERBOSE)
+      { fprintf(stderr,"\n  The input table is");
+        if (trim)
+          if (symm)
+            fprintf(stderr," trimmed and symmetric\n");
+          else
+            fprintf(stderr," trimmed but not symmetric\n");
+        else
+          if (symm)
+            fprintf(stderr," untrimmed yet symmetric\n");
+          else
+            fprintf(stderr," untrimmed and not symmetric\n");
+      }
+
+    sprintf(tname,"%s",SRC);
+
+    if (!trim)
+      { if (VERBOSE)
+          { fprintf(stderr,"\n  Trimming k-mers in table with count < %d\n",ETHRESH);
+            fflush(stderr);
+          }
+        sprintf(command,"Logex -T%d '%s.trim=A[%d-]' %s",NTHREADS,troot,ETHRESH,tname);
+        systemx(command);
+        sprintf(tname,"%s.trim",troot);
+      }
+
+    if (!symm)
+      { if (VERBOSE)
+          { if (trim)
+              fprintf(stderr,"\n  Making table symmetric\n");
+            else
+              fprintf(stderr,"\n  Making trimmed table symmetric\n");
+            fflush(stderr);
+          }
+        sprintf(command,"Symmex -T%d -P%s %s %s.symx",NTHREADS,SORT_PATH,tname,troot);
+        systemx(command);
+        if (!trim)
+          { sprintf(command,"Fastrm %s.trim",troot);
+            systemx(command);
+          }
+        sprintf(tname,"%s.symx",troot);
+      }
+
+    free(command);
+    if (!(symm && trim))
+      { input = tname;
+        hm_scan_destroy(S);
+        hm_table_close(T);
+        if (hm_table_open(input,&T) != HM_OK)
+          { fprintf(stderr,"%s: Cannot open k-mer table %s\n",Prog_Name,input);
+            exit (1);
+          }
+        if (hm_scan_create(hm_table_view(T),devs,ngpu,&S) != HM_OK)
+          die_hm();
+      }
+    else
+      free(tname);
+  }
+
+  if (VERBOSE)
+    { fprintf(stderr,"\n  Starting to count covariant pairs\n");
+      fflush(stderr);
+    }
+
+  int64_t      *PLOT = malloc(sizeof(int64_t)*HM_PLOT_CELLS);
+  hm_scan_stats stats;
+  if (PLOT == NULL)
+    { fprintf(stderr,"%s: Out of memory (Allocating plot)\n",Prog_Name);
+      exit (1);
+    }
+  if (hm_scan_run(S,PLOT,&stats) != HM_OK)
+    die_hm();
+  hm_scan_destroy(S);
+  hm_table_close(T);
+
+  if (getenv("HETMERS_STATS") != NULL)
+    fprintf(stderr,"{\"nels\": %lld, \"n_gpus\": %d, \"bucket_bits\": %d, \"ms_load\": %.3f, "
+                   "\"ms_pass1\": %.3f, \"ms_pass2\": %.3f, \"ms_scan\": %.3f, \"kernel_launches\": %lld}\n",
+            (long long) stats.nels,stats.n_gpus,stats.bucket_bits,stats.ms_h2d_unpack,
+            stats.ms_pass1,stats.ms_pass2,stats.ms_scan,(long long) stats.kernel_launches);
+
+  if (input != NULL)                                              /* PloidyPlot.c:1584-1592 */
+    { char *command = malloc(strlen(input)+100);
+      if (command == NULL)
+        exit (1);
+      sprintf(command,"Fastrm %s",input);
+      systemx(command);
+      free(command);
+      free(input);
+    }
+
+  if (VERBOSE)
+    { fprintf(stderr,"\n  Count complete, outputting table\n");
+      fflush(stderr);
+    }
+
+  { char *smu = malloc(strlen(OUT)+8);
+    sprintf(smu,"%s.smu",OUT);
+    if (hm_write_smu(smu,PLOT) != HM_OK)
+      { fprintf(stderr,"Could not open %s.smu\n",OUT);
+        exit (1);
+      }
+    free(smu);
+  }
+
+  free(PLOT);
+  free(OUT);
+  exit (0);
+}

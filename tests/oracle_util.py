@@ -1,0 +1,95 @@
+"""Test-side access to the CPU checkers (oracle/ is test infrastructure only):
+  * liboracle.so  -- oracle/hetmers_oracle.c, the C restatement of the reference algorithm
+  * oracle/_ref/hetmers -- the unmodified reference binary, when it has been built
+  * brute_force() -- SURVEY.md Appendix B, an independent 15-line definition (tiny inputs only)
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "hetmers")
+SMAX, FMAX, PLOT_W = 1000, 500, 501
+PLOT_CELLS = 1001 * 501
+
+_lib = None
+
+
+def oracle_lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_SO):
+            subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so", "hetmers_oracle"], check=True)
+        L = C.CDLL(ORACLE_SO)
+        L.oracle_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+        L.oracle_hetmers_file.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_int),
+                                          C.POINTER(C.c_int), C.POINTER(C.c_int64)]
+        _lib = L
+    return _lib
+
+
+def oracle_scan(keys_bytes: np.ndarray, cnt: np.ndarray, kmer: int):
+    """keys_bytes uint8[n,kbyte] sorted; -> (plot int64[1001,501], deg uint8[n])"""
+    L = oracle_lib()
+    keys_bytes = np.ascontiguousarray(keys_bytes, dtype=np.uint8)
+    cnt = np.ascontiguousarray(cnt, dtype=np.uint16)
+    n = keys_bytes.shape[0]
+    plot = np.zeros(PLOT_CELLS, dtype=np.int64)
+    deg = np.zeros(max(n, 1), dtype=np.uint8)
+    rc = L.oracle_scan(keys_bytes.ctypes.data, cnt.ctypes.data, n, kmer, plot.ctypes.data, deg.ctypes.data)
+    assert rc == 0
+    return plot.reshape(SMAX + 1, PLOT_W), deg[:n]
+
+
+def oracle_file(table: str, ethresh: int, smu_path: str):
+    """-> (rc, trim, symm, nels); rc 0 ok / 1 cannot open / 2 needs conditioning"""
+    L = oracle_lib()
+    trim, symm, nels = C.c_int(-1), C.c_int(-1), C.c_int64(0)
+    rc = L.oracle_hetmers_file(table.encode(), ethresh, smu_path.encode(), C.byref(trim), C.byref(symm), C.byref(nels))
+    return rc, trim.value, symm.value, nels.value
+
+
+def have_ref():
+    return os.path.exists(REF_BIN) and os.access(REF_BIN, os.X_OK)
+
+
+def run_ref(table: str, out: str, ethresh: int, threads: int = 4, verbose=False):
+    """run the unmodified reference binary; returns CompletedProcess (output in out + '.smu')"""
+    if os.path.exists(out + ".smu"):
+        os.remove(out + ".smu")
+    cmd = [REF_BIN, f"-e{ethresh}", f"-T{threads}", f"-o{out}", table]
+    if verbose:
+        cmd.insert(1, "-v")
+    return subprocess.run(cmd, input="n\n", capture_output=True, text=True)
+
+
+def smu_text(plot) -> str:
+    p = np.asarray(plot).reshape(SMAX + 1, PLOT_W)[:, :FMAX]
+    s, m = np.nonzero(p > 0)
+    return "".join(f"{mi}\t{si - mi}\t{p[si, mi]}\n" for si, mi in zip(s.tolist(), m.tolist()))
+
+
+def brute_force(keys_u64: np.ndarray, cnt: np.ndarray, k: int):
+    """SURVEY.md Appendix B on left-aligned uint64 keys (python ints; n <~ 2e4)."""
+    tab = {int(x): int(c) for x, c in zip(keys_u64.tolist(), cnt.tolist())}
+    deg = {x: 0 for x in tab}
+    pairs = []
+    for x, cx in tab.items():
+        for p in range(k):
+            sh = 62 - 2 * p
+            b = (x >> sh) & 3
+            for alt in range(b + 1, 4):
+                y = x + ((alt - b) << sh)
+                cy = tab.get(y)
+                if cy is not None and cx + cy <= SMAX:
+                    deg[x] = (deg[x] + 1) & 0xFF
+                    deg[y] = (deg[y] + 1) & 0xFF
+                    pairs.append((x, y))
+    plot = np.zeros((SMAX + 1, PLOT_W), dtype=np.int64)
+    for x, y in pairs:
+        if deg[x] <= 1 and deg[y] <= 1:
+            plot[tab[x] + tab[y], min(tab[x], tab[y])] += 1
+    return plot, np.array([deg[int(x)] for x in keys_u64.tolist()], dtype=np.uint8)

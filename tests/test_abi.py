@@ -1,0 +1,97 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol the header
+declares, and the `hetmers` executable honours the reference's argv / message / exit-code
+contract (PloidyPlot.c:1246-1314,1350-1354; gene_core.h:32-56) for the cases that need no GPU."""
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import GOLDEN, ROOT
+from smudgeplot_b200 import _lib, hetmers
+
+
+def test_library_loads_and_exports_header_symbols(built):
+    L = _lib.lib()
+    hdr = open(os.path.join(ROOT, "include", "hetmers_b200.h")).read()
+    declared = set(re.findall(r"\b(hm_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"hm_last_error"} - {"hm_last_error"}
+    assert declared, "no declarations parsed"
+    for sym in sorted(declared):
+        assert hasattr(L, sym), f"{sym} declared in hetmers_b200.h but not exported"
+    assert declared == set(_lib.ABI_SYMBOLS)
+    assert L.hm_abi_version() == 1
+    assert L.hm_pick_bucket_bits(200_000_000) == 26
+    assert L.hm_pick_bucket_bits(1) == 2
+
+
+def run(*args, stdin="n\n"):
+    return subprocess.run([_lib.BIN_PATH, *args], input=stdin, capture_output=True, text=True)
+
+
+def test_usage_on_wrong_positional_count(built):
+    for argv in ([], ["a", "b"]):
+        r = run(*argv)
+        assert r.returncode == 1
+        assert r.stderr.startswith("\nUsage: hetmers  [-v] [-T<int(4)>] [-P<dir(/tmp)>]\n")
+        assert "-e: count threshold below which k-mers are considered erroneous" in r.stderr
+        assert r.stdout == ""
+
+
+def test_illegal_option_and_bad_integers(built):
+    r = run("-x", "tab")
+    assert (r.returncode, r.stderr) == (1, "hetmers: -x is an illegal option\n")
+    r = run("-vq", "tab")
+    assert (r.returncode, r.stderr) == (1, "hetmers: -q is an illegal option\n")
+    r = run("-eabc", "tab")
+    assert (r.returncode, r.stderr) == (1, "hetmers: -e 'abc' argument is not an integer\n")
+    r = run("-T0", "tab")
+    assert (r.returncode, r.stderr) == (1, "hetmers: Number of threads must be positive (0)\n")
+    r = run("-e-3", "tab")
+    assert (r.returncode, r.stderr) == (1, "hetmers: Error-mer threshold must be positive (-3)\n")
+
+
+def test_missing_table_message_and_thread_clamp(built, tmp_path):
+    r = run("-T100", "-vklfs", f"-o{tmp_path}/o", str(tmp_path / "absent"))
+    assert r.returncode == 1
+    assert r.stderr == ("hetmers: Warning, only 64 threads will be used\n"
+                        f"hetmers: Cannot open k-mer table {tmp_path}/absent\n")
+
+
+def test_existing_smu_prompt_reuse(built, tmp_path):
+    out = tmp_path / "have"
+    (tmp_path / "have.smu").write_text("1\t2\t3\n")
+    r = run(f"-o{out}", os.path.join(GOLDEN, "dip_k21", "dip_k21"), stdin="yes please\n")
+    assert r.returncode == 0
+    assert r.stdout == f"\n  Found het-table {out}.smu, use it? "
+    assert r.stderr == "\n  Using the found het-table, done\n"
+    assert (tmp_path / "have.smu").read_text() == "1\t2\t3\n"          # untouched
+
+
+def test_missing_part_file_is_reported(built, tmp_path):
+    import shutil
+    d = tmp_path / "g"
+    shutil.copytree(os.path.join(GOLDEN, "trip_k31"), d)
+    os.remove(d / ".trip_k31.ktab.3")
+    r = run(f"-o{tmp_path}/o", str(d / "trip_k31"))
+    assert r.returncode == 1 and "Table part" in r.stderr and "is missing ?" in r.stderr
+
+
+def test_cli_argv_mirror_of_reference_cli():
+    # cli.py:350-359
+    assert hetmers.hetmers_args("t.ktab", o="out", L=12, t=4) == ["-oout", "-e12", "-T4", "t.ktab"]
+    assert hetmers.hetmers_args("t", o="o", L=3, t=8, verbose=True, tmp="/scratch") == \
+        ["-oo", "-e3", "-T8", "-v", "-P/scratch", "t"]
+    with pytest.raises(ValueError):
+        hetmers.hetmers_args("t")
+
+
+def test_no_gpu_means_loud_failure(built, tmp_path):
+    L = _lib.lib()
+    if L.hm_device_count() > 0:
+        pytest.skip("a GPU is visible here")
+    r = run(f"-o{tmp_path}/o", os.path.join(GOLDEN, "dip_k21", "dip_k21"))
+    assert r.returncode == 1 and "no CUDA device" in r.stderr and not (tmp_path / "o.smu").exists()
+    from smudgeplot_b200 import fastk
+    with pytest.raises(_lib.HetmersError):
+        hetmers.scan_table(fastk.read_ktab(os.path.join(GOLDEN, "dip_k21", "dip_k21")))

@@ -1,0 +1,227 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI of
+libhetmers_b200.so (in-process via ctypes, or through the drop-in `hetmers` executable) and is
+compared bit for bit with (a) the golden .smu files written by the unmodified reference binary,
+(b) the oracle on seeded tables, (c) the reference binary itself when oracle/_ref/hetmers is
+present, and (d) size-independent properties at BASELINE.json's full size."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_cases
+import oracle_util as ou
+from smudgeplot_b200 import _lib, fastk, hetmers
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu(built):
+    assert _lib.lib().hm_device_count() >= 1, "these tests need a CUDA device (no CPU fallback exists)"
+
+
+def _golden(name):
+    return os.path.join(GOLDEN, name, name)
+
+
+# ------------------------------------------------------------------ (a) golden vectors ------
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_executable_reproduces_reference_smu(name, golden_meta, tmp_path):
+    c = golden_meta[name]
+    out = str(tmp_path / "out")
+    r = subprocess.run([_lib.BIN_PATH, "-v", f"-e{c['e']}", "-T4", f"-o{out}", _golden(name)],
+                       input="n\n", capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == ""
+    assert r.stderr == ("\n  The input table is trimmed and symmetric\n"
+                        "\n  Starting to count covariant pairs\n"
+                        "\n  Count complete, outputting table\n")       # the reference's -v lines
+    assert open(out + ".smu").read() == open(_golden(name) + ".smu").read()
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_inprocess_scan_reproduces_reference_smu_and_oracle_deg(name, golden_meta):
+    c = golden_meta[name]
+    kt = fastk.read_ktab(_golden(name))
+    kb, cn = fastk.unpack_host(kt)
+    with hetmers.Scan(kt) as sc:
+        assert sc.examine(c["e"]) == (True, True)
+        plot, stats = sc.run()
+        keys, cnt, deg = sc.download()
+    assert hetmers.smu_text(plot) == open(_golden(name) + ".smu").read()
+    assert np.array_equal(keys, fastk.keys_bytes_to_u64(kb))            # GPU unpack == host unpack
+    assert np.array_equal(cnt, cn)
+    want_plot, want_deg = ou.oracle_scan(kb, cn, kt.kmer)
+    assert np.array_equal(deg, want_deg)                                # pass-1 incidence array
+    assert np.array_equal(plot, want_plot)                              # incl. the dropped m=500 column
+    assert stats["nels"] == c["nels"] and stats["kernel_launches"] >= 4
+
+
+def test_default_output_root_and_ktab_suffix(tmp_path):
+    d = tmp_path / "g"
+    shutil.copytree(os.path.join(GOLDEN, "dip_k21"), d)
+    r = subprocess.run([_lib.BIN_PATH, str(d / "dip_k21.KTAB")], input="n\n", capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr                                  # default -e4, -T4
+    assert (d / "dip_k21.smu").read_text() == open(_golden("dip_k21") + ".smu").read()
+    # second run: file exists -> prompt; "n" recomputes, "y" leaves it
+    r = subprocess.run([_lib.BIN_PATH, str(d / "dip_k21")], input="n\n", capture_output=True, text=True)
+    assert r.returncode == 0 and "Found het-table" in r.stdout
+
+
+# ------------------------------------------------------------------ conditioning verdicts ----
+
+@pytest.mark.parametrize("name,verdict,tool", [("untrimmed", (False, True), "Logex"),
+                                               ("asymmetric", (True, False), "Symmex")])
+def test_examine_table_decisions(name, verdict, tool, golden_meta, tmp_path):
+    c = golden_meta["_conditioning"][name]
+    table = os.path.join(GOLDEN, "conditioning", name)
+    with hetmers.Scan(fastk.read_ktab(table)) as sc:
+        assert sc.examine(c["e"]) == verdict
+    # the executable prints the reference's verdict and then shells out to the same FastK tool
+    r = subprocess.run([_lib.BIN_PATH, "-v", f"-e{c['e']}", "-T4", f"-o{tmp_path}/o", table],
+                       input="n\n", capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 1
+    assert c["verbose"][0] in r.stderr
+    if shutil.which(tool) is None:
+        want = c["stderr_tail"][0].replace("/root/repo/tests/golden", GOLDEN)
+        assert want in r.stderr                                         # "hetmers: Command '...' failed"
+
+
+# ------------------------------------------------------------------ (b) seeded tables vs oracle
+
+CASES = [  # k, G, ploidy, het, cov, L, seed, ibyte, nparts
+    (13, 60000, 2, 0.02, 40, 4, 101, 3, 1),
+    (21, 80000, 2, 0.01, 40, 4, 1, 3, 2),
+    (27, 50000, 4, 0.02, 80, 10, 102, 2, 3),
+    (31, 100000, 3, 0.01, 60, 12, 4, 3, 4),
+    (32, 40000, 2, 0.03, 40, 4, 103, 3, 1),
+    (12, 200000, 2, 0.02, 30, 4, 104, 3, 2),      # kbyte == ibyte: records are counts only
+    (4, 300, 2, 0.2, 30, 1, 105, 1, 1),           # tiny k, saturated neighbourhoods
+]
+
+
+@pytest.mark.parametrize("k,G,ploidy,het,cov,L,seed,ibyte,nparts", CASES)
+def test_seeded_table_matches_oracle(k, G, ploidy, het, cov, L, seed, ibyte, nparts, tmp_path):
+    keys, cnt = synth.synth_table(k, G, ploidy, het, cov, L, seed, extra_hom_repeats=1)
+    name = str(tmp_path / "t")
+    kt = synth.write_table(name, k, keys, cnt, ibyte=ibyte, nparts=nparts)
+    kb, cn = fastk.unpack_host(kt)
+    want_plot, want_deg = ou.oracle_scan(kb, cn, k)
+    with hetmers.Scan(fastk.read_ktab(name)) as sc:
+        plot, _ = sc.run()
+        _, _, deg = sc.download()
+    assert np.array_equal(deg, want_deg)
+    assert np.array_equal(plot, want_plot)
+    plot2, _ = hetmers.scan_table(kt)                                   # one-call route
+    assert np.array_equal(plot2, want_plot)
+
+
+def test_two_entry_and_pairless_tables(tmp_path):
+    # smallest legal table (nels >= 2) and a table without any one-away pair
+    k = 21
+    keys = np.array([0x0123456789AB << 16, (0x0123456789AB << 16) + (1 << 22)], dtype=np.uint64)
+    for cn, rows in (([5, 9], "5\t9\t1\n"), ([600, 500], "")):
+        name = str(tmp_path / f"t{cn[0]}")
+        kt = fastk.write_ktab(name, k, keys, np.array(cn, dtype=np.uint16), ibyte=3)
+        plot, _ = hetmers.scan_table(kt)
+        assert hetmers.smu_text(plot) == rows
+    far = np.array([1 << 30, 7 << 40, 9 << 50], dtype=np.uint64)
+    kt = fastk.write_ktab(str(tmp_path / "far"), k, far, np.array([9, 9, 9], dtype=np.uint16), ibyte=2)
+    plot, _ = hetmers.scan_table(kt)
+    assert plot.sum() == 0
+
+
+def test_result_independent_of_bucket_bits_and_work_split():
+    """layer A on torch tensors: any bucket width and any split of the index range into work
+    ranges (the multi-GPU sharding) gives the same plot."""
+    import torch
+    from smudgeplot_b200.device import DeviceTable
+    keys, cnt = synth.synth_table(25, 60000, 3, 0.02, 60, 8, 77, device="cuda")
+    c16 = cnt.to(torch.int16)
+    ref = None
+    for bits in (2, 9, 15, 20):
+        t = DeviceTable(25, keys, c16, bits=bits).build_index()
+        p = t.scan().clone()
+        ref = p if ref is None else ref
+        assert torch.equal(p, ref)
+    n = keys.numel()
+    t = DeviceTable(25, keys, c16).build_index()
+    cuts = [0, n // 7, n // 2, n - 3, n]
+    deg = torch.zeros((n + 4) & ~3, dtype=torch.uint8, device="cuda")
+    parts = []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        w = DeviceTable(25, keys, c16)
+        w.bucket = t.bucket
+        w.alloc_work(lo, hi)
+        w.deg = deg                       # shared incidence array == result of the all-reduce
+        w.pass1()
+        parts.append(w)
+    plot = torch.zeros_like(ref).view(-1)
+    for w in parts:
+        w.plot = plot
+        w.pass2()
+    torch.cuda.synchronize()
+    assert torch.equal(plot.view_as(ref), ref)
+
+
+# ------------------------------------------------------------------ (c) vs the reference binary
+
+@pytest.mark.parametrize("k,target,ploidy,het,cov,L,seed", [(21, 1_000_000, 2, 0.01, 40, 4, 1),      # BASELINE config 1
+                                                           (31, 20_000_000, 2, 0.01, 40, 12, 2)])   # config 2 at 1/10
+def test_medium_table_matches_reference_binary(k, target, ploidy, het, cov, L, seed, tmp_path):
+    G = synth.calibrate_G(k, target, ploidy, het, cov, L)
+    keys, cnt = synth.synth_table(k, G, ploidy, het, cov, L, seed, device="cuda")
+    name = str(tmp_path / "t")
+    kt = synth.write_table(name, k, keys, cnt, ibyte=3, nparts=4)
+    assert abs(kt.nels - target) < 0.1 * target
+    out = str(tmp_path / "gpu")
+    hetmers.run_hetmers(name, o=out, L=L, t=4)
+    got = open(out + ".smu").read()
+    if ou.have_ref():
+        r = ou.run_ref(name, str(tmp_path / "ref"), L, threads=min(os.cpu_count() or 4, 64))
+        assert r.returncode == 0, r.stderr
+        want = open(str(tmp_path / "ref.smu")).read()
+    else:
+        rc, *_ = ou.oracle_file(name, L, str(tmp_path / "ora.smu"))
+        assert rc == 0
+        want = open(str(tmp_path / "ora.smu")).read()
+    assert got == want and len(got) > 0
+
+
+# ------------------------------------------------------------------ (d) full-size properties --
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 (k=31, ~2e8 k-mers, diploid het 1%, cov 40, L=12) on one GPU.
+    Size-independent properties of a symmetric table with symmetric counts:
+      * deg[rc(x)] == deg[x]  (a neighbour at base p of x is a neighbour at base k-1-p of rc(x):
+        ties the low-position search, whose partners are ~n/4^p entries away, to the
+        high-position search, whose partners are adjacent)
+      * sum(plot) == #{x : deg[x]==1 and deg[partner(x)]==1} / 2, recounted with torch ops
+      * the plot does not change when the scan is repeated (idempotence / no stale state)"""
+    import torch
+    from smudgeplot_b200.device import DeviceTable
+    k, L = 31, 12
+    G = synth.calibrate_G(k, 200_000_000, 2, 0.01, 40, L)
+    keys, cnt = synth.synth_table(k, G, 2, 0.01, 40, L, 2, device="cuda")
+    n = keys.numel()
+    assert abs(n - 2e8) < 2e7
+    t = DeviceTable(k, keys, cnt.to(torch.int16)).build_index()
+    plot = t.scan().clone()
+    deg = t.deg[:n].clone()
+    plot_again = t.scan()
+    assert torch.equal(plot, plot_again)
+    rc = synth.revcomp_left(keys, k)
+    pos = t.find(rc)
+    assert bool((pos >= 0).all())
+    assert torch.equal(deg[pos], deg)
+    up = t.up.long()
+    has = (deg == 1) & (up >= 0)            # -1 == the all-ones 'none' marker
+    idx = torch.nonzero(has).squeeze(1)
+    iso = deg[up[idx]] == 1
+    assert int(iso.sum()) == int(plot.sum())
+    # every isolated pair has an isolated mirror pair (rc), so hom/het structure is strand-symmetric
+    assert int(plot.sum()) > 0.1 * n * 0.5 * 0.2
