@@ -1,0 +1,188 @@
+"""One-process-per-GPU sharding of the hetmers scan (torch.distributed = plumbing; NCCL over
+NVLink/NVSwitch on GPUs, gloo in the CPU tests of the host logic).
+
+Path partition: the sorted table is cut into `world` contiguous
+shards on prefix-bucket boundaries ("canonical-prefix buckets" of BASELINE.json's north_star).
+Rank r loads / owns shard r, every rank ends with a full replica (shards broadcast over NVLink),
+and rank r scans index range [lo_r, hi_r):
+
+    pass 1 (own range, lower pair member does the book-keeping)  -> partial incidence array
+    all-reduce(sum, uint8[n])                                    <- the one real exchange step
+    pass 2 (own range)                                           -> partial plot
+    all-reduce(sum, int64[1001*501])                             <- the reference's serial
+                                                                    plot reduction, :1569-1575
+The reference has no multi-process code at all; its only "collective" is that final sum.
+"""
+from __future__ import annotations
+
+import time
+
+import torch
+import torch.distributed as dist
+
+
+def prefix_partition(world: int, bits: int = 24):
+    """equal split of the `bits`-bit prefix space: [(lo_r, hi_r)] for r in range(world)"""
+    top = 1 << bits
+    return [((top * r) // world, (top * (r + 1)) // world) for r in range(world)]
+
+
+def shard_offsets(local_n: int, group=None, device=None):
+    """all ranks' shard sizes -> (sizes list, offsets list, total)"""
+    world = dist.get_world_size(group)
+    t = torch.zeros(world, dtype=torch.int64, device=device)
+    t[dist.get_rank(group)] = local_n
+    dist.all_reduce(t, group=group)
+    sizes = [int(x) for x in t.tolist()]
+    offs = [0]
+    for s in sizes:
+        offs.append(offs[-1] + s)
+    return sizes, offs[:-1], offs[-1]
+
+
+def gather_table(local_keys: torch.Tensor, local_cnt: torch.Tensor, group=None, out=None):
+    """Assemble the full sorted table on every rank from per-rank shards (shard r = rank r's
+    slice of the key space, so concatenation in rank order is the sorted table).
+    -> (keys_full, cnt_full, lo, hi) with [lo,hi) this rank's index range."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes, offs, total = shard_offsets(local_keys.numel(), group, local_keys.device)
+    if out is None:
+        keys = torch.empty(total, dtype=local_keys.dtype, device=local_keys.device)
+        cnt = torch.empty(total, dtype=local_cnt.dtype, device=local_cnt.device)
+    else:
+        keys, cnt = out
+    lo, hi = offs[rank], offs[rank] + sizes[rank]
+    if local_keys.data_ptr() != keys[lo:hi].data_ptr():
+        keys[lo:hi].copy_(local_keys)
+        cnt[lo:hi].copy_(local_cnt)
+    for r in range(world):
+        if sizes[r] == 0:
+            continue
+        src = dist.get_global_rank(group, r) if group is not None else r
+        dist.broadcast(keys[offs[r]:offs[r] + sizes[r]], src=src, group=group)
+        # counts travel as raw bytes (gloo has no int16 broadcast; NCCL does not care)
+        dist.broadcast(cnt[offs[r]:offs[r] + sizes[r]].view(torch.uint8), src=src, group=group)
+    return keys, cnt, lo, hi
+
+
+def allreduce_deg(deg: torch.Tensor, group=None):
+    """sum of the partial incidence arrays (uint8; no wrap: <= 3k <= 96 neighbours for k <= 32)"""
+    dist.all_reduce(deg, op=dist.ReduceOp.SUM, group=group)
+    return deg
+
+
+def allreduce_plot(plot: torch.Tensor, group=None):
+    dist.all_reduce(plot, op=dist.ReduceOp.SUM, group=group)
+    return plot
+
+
+class ShardedScan:
+    """device-resident replica + this rank's work range; `scan()` = T_scan of SURVEY.md §8d"""
+
+    def __init__(self, kmer, keys_full, cnt_full, lo, hi, group=None):
+        from .device import DeviceTable
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.table = DeviceTable(kmer, keys_full, cnt_full).build_index()
+        self.table.alloc_work(lo, hi)
+        self.kmer, self.lo, self.hi = kmer, lo, hi
+        self.n_total = keys_full.numel()
+        self.bits = self.table.bits
+        self._shard_src = None
+
+    @classmethod
+    def from_synthetic(cls, k, G, ploidy, het, cov, L, seed, device, group=None):
+        """every rank generates only its prefix-range shard of the seeded table, then the shards
+        are exchanged (same flow as loading 1/world of the part files per rank)."""
+        from tools import synth
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        rng = prefix_partition(world)[rank]
+        keys, cnt = synth.synth_table(k, G, ploidy, het, cov, L, seed, device=device, key_range=rng)
+        cnt16 = cnt.to(torch.int16)
+        del cnt
+        kf, cf, lo, hi = gather_table(keys, cnt16, group)
+        del keys, cnt16
+        return cls(k, kf, cf, lo, hi, group)
+
+    def scan(self, events=None):
+        t = self.table
+        t.deg.zero_()
+        t.plot.zero_()
+        if events is not None:
+            events[0].record()
+        t.pass1()
+        if events is not None:
+            events[1].record()
+        allreduce_deg(t.deg, self.group)
+        t.pass2()
+        allreduce_plot(t.plot, self.group)
+        return t.plot
+
+    # ---- end-to-end from pinned host buffers (bench.py e2e leg) -----------------------------
+    def measure_e2e(self, steps, warmup):
+        """per step: H2D of this rank's shard of raw FastK records + the stub index, unpack,
+        shard exchange, bucket index, scan, plot D2H on rank 0.  -> e2e dict (max over ranks)."""
+        from . import _lib
+        from .device import DeviceTable
+        t = self.table
+        dev = t.device
+        k, n, lo, hi = self.kmer, self.n_total, self.lo, self.hi
+        kbyte, ibyte = (k + 3) // 4, 3
+        pbyte = kbyte - ibyte + 2
+        m = hi - lo
+        keys, cnt = t.keys, t.cnt
+        rec = torch.empty((m, pbyte), dtype=torch.uint8, device=dev)
+        ks, cs = keys[lo:hi], cnt[lo:hi].to(torch.int32) & 0xFFFF
+        for j in range(ibyte, kbyte):
+            rec[:, j - ibyte] = ((ks >> (56 - 8 * j)) & 0xFF).to(torch.uint8)
+        rec[:, pbyte - 2] = (cs & 0xFF).to(torch.uint8)
+        rec[:, pbyte - 1] = ((cs >> 8) & 0xFF).to(torch.uint8)
+        index = torch.cumsum(torch.bincount((keys >> 40) & 0xFFFFFF, minlength=1 << 24), 0)
+        h_rec = torch.empty(rec.numel(), dtype=torch.uint8, pin_memory=True)
+        h_rec.copy_(rec.view(-1))
+        h_idx = torch.empty(1 << 24, dtype=torch.int64, pin_memory=True)
+        h_idx.copy_(index)
+        h_plot = torch.empty(_lib.PLOT_CELLS, dtype=torch.int64, pin_memory=True)
+        del rec, index, ks, cs
+        # the replica built by the timed call reuses no state of self.table
+        d_rec = torch.empty(h_rec.numel(), dtype=torch.uint8, device=dev)
+        d_idx = torch.empty(1 << 24, dtype=torch.int64, device=dev)
+        k2 = torch.empty(n, dtype=torch.int64, device=dev)
+        c2 = torch.empty(n, dtype=torch.int16, device=dev)
+
+        def call():
+            d_rec.copy_(h_rec, non_blocking=True)
+            d_idx.copy_(h_idx, non_blocking=True)
+            DeviceTable.from_records(k, ibyte, d_rec, d_idx, first=lo, out=(k2, c2))
+            gather_table(k2[lo:hi], c2[lo:hi], self.group, out=(k2, c2))
+            tt = DeviceTable(k, k2, c2, bits=self.bits).build_index()
+            tt.alloc_work(lo, hi)
+            tt.pass1()
+            allreduce_deg(tt.deg, self.group)
+            tt.pass2()
+            allreduce_plot(tt.plot, self.group)
+            if self.rank == 0:
+                h_plot.copy_(tt.plot, non_blocking=True)
+            torch.cuda.synchronize()
+            return tt
+
+        for _ in range(max(warmup, 1)):
+            call()
+        dist.barrier(self.group)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            tt = call()
+        dist.barrier(self.group)
+        dt = torch.tensor([(time.perf_counter() - t0) / steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX, group=self.group)
+        same = bool(torch.equal(tt.plot, t.plot)) if steps > 0 else True
+        dtv = float(dt.item())
+        h2d = torch.tensor([h_rec.numel() + h_idx.numel() * 8], dtype=torch.int64, device=dev)
+        dist.all_reduce(h2d, group=self.group)                     # whole job, all ranks
+        return {"value": n / dtv, "unit": "k-mers/s", "ms_per_step": dtv * 1e3,
+                "h2d_bytes_per_step": int(h2d.item()),
+                "d2h_bytes_per_step": int(_lib.PLOT_CELLS * 8),
+                "api": "smudgeplot_b200.dist: pinned shard records -> H2D -> hm_k_unpack_records -> shard broadcast "
+                       "(NCCL) -> hm_k_build_bucket_index -> pass1 -> all-reduce(deg) -> pass2 -> all-reduce(plot) -> D2H",
+                "plot_matches_resident_scan": same}

@@ -93,3 +93,36 @@ def brute_force(keys_u64: np.ndarray, cnt: np.ndarray, k: int):
         if deg[x] <= 1 and deg[y] <= 1:
             plot[tab[x] + tab[y], min(tab[x], tab[y])] += 1
     return plot, np.array([deg[int(x)] for x in keys_u64.tolist()], dtype=np.uint8)
+
+
+# ---- range-restricted restatement of the two kernels' contracts (multi-GPU host-logic tests) ----
+
+def partial_pass1(keys_u64: np.ndarray, cnt: np.ndarray, k: int, lo: int, hi: int):
+    """what hm_k_pass1_degree contributes for the work range [lo,hi): partial incidence array over
+    the WHOLE table (lower pair member books both ends) and up[x-lo] = index of the upper partner."""
+    pos = {int(x): i for i, x in enumerate(keys_u64.tolist())}
+    deg = np.zeros(len(keys_u64), dtype=np.uint8)
+    up = np.full(hi - lo, -1, dtype=np.int64)
+    for i in range(lo, hi):
+        x, cx = int(keys_u64[i]), int(cnt[i])
+        for p in range(k):
+            sh = 62 - 2 * p
+            b = (x >> sh) & 3
+            for alt in range(b + 1, 4):
+                j = pos.get(x + ((alt - b) << sh))
+                if j is not None and cx + int(cnt[j]) <= SMAX:
+                    deg[i] += 1
+                    deg[j] += 1
+                    up[i - lo] = j
+    return deg, up
+
+
+def partial_pass2(cnt: np.ndarray, deg: np.ndarray, up: np.ndarray, lo: int, hi: int):
+    """what hm_k_pass2_plot adds for [lo,hi) given the SUMMED incidence array"""
+    plot = np.zeros((SMAX + 1, PLOT_W), dtype=np.int64)
+    for i in range(lo, hi):
+        j = int(up[i - lo])
+        if deg[i] <= 1 and j >= 0 and deg[j] <= 1:
+            ci, cj = int(cnt[i]), int(cnt[j])
+            plot[ci + cj, min(ci, cj)] += 1
+    return plot

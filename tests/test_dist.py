@@ -1,0 +1,80 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic in smudgeplot_b200/dist.py: prefix
+partition, shard exchange, the incidence all-reduce between the passes and the final plot
+all-reduce.  The per-rank compute is stood in for by oracle_util.partial_pass1/2 (test
+infrastructure restating the two kernels' contracts); the result must equal the oracle's
+single-process plot."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+K, G, P, HET, COV, L, SEED = 17, 1200, 3, 0.03, 60, 8, 5
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle_util as ou
+        from smudgeplot_b200 import dist as hd
+        from tools import synth
+        rng = hd.prefix_partition(world)[rank]
+        keys, cnt = synth.synth_table(K, G, P, HET, COV, L, SEED, key_range=rng)
+        kf, cf, lo, hi = hd.gather_table(keys, cnt.to(torch.int16))
+        ku = kf.numpy().view(np.uint64)
+        cn = cf.numpy().view(np.uint16)
+        deg_part, up = ou.partial_pass1(ku, cn, K, lo, hi)
+        deg = torch.from_numpy(deg_part.copy())
+        hd.allreduce_deg(deg)
+        plot = torch.from_numpy(ou.partial_pass2(cn, deg.numpy(), up, lo, hi).reshape(-1).copy())
+        hd.allreduce_plot(plot)
+        q.put((rank, lo, hi, ku.copy(), cn.copy(), deg.numpy().copy(), plot.numpy().copy()))
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_scan_host_logic_gloo(world):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_util as ou
+    from smudgeplot_b200 import fastk
+    from tools import synth
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    keys, cnt = synth.synth_table(K, G, P, HET, COV, L, SEED)
+    ku = synth.keys_to_u64_numpy(keys)
+    cn = cnt.numpy().astype(np.uint16)
+    want_plot, want_deg = ou.oracle_scan(fastk.keys_u64_to_bytes(ku, K), cn, K)
+    cover = 0
+    for rank, lo, hi, k2, c2, deg, plot in res:
+        assert np.array_equal(k2, ku) and np.array_equal(c2, cn)       # every rank holds the full sorted table
+        assert np.array_equal(deg, want_deg)                           # summed incidence array == Pair
+        assert np.array_equal(plot.reshape(want_plot.shape), want_plot)
+        assert lo == cover
+        cover = hi
+    assert cover == len(ku)
+
+
+def test_prefix_partition_tiles_the_prefix_space():
+    from smudgeplot_b200 import dist as hd
+    for w in (1, 2, 3, 8):
+        parts = hd.prefix_partition(w)
+        assert parts[0][0] == 0 and parts[-1][1] == 1 << 24
+        assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
