@@ -185,71 +185,264 @@ extern "C" int hm_k_build_bucket_index(const uint64_t *d_keys, int64_t n, int bi
   return HM_OK;
 }
 
+/* ------------------------------------------------------------------ prefix filter ------- */
+
+/* Presence bitmap over the first 2*PH bits (PH bases) of every key: bit f set iff some table
+ * entry starts with f.  ~16 bits per entry: a probe for a k-mer that is NOT in
+ * the table -- 99 % of all probes -- is answered by one 4-byte load that neighbouring lanes
+ * share, instead of a bucket lookup + bisection.                                              */
+__global__ void __launch_bounds__(256)
+filter_build_kernel(const uint64_t *__restrict__ keys, int64_t n, int fshift,
+                    uint32_t *__restrict__ filter)
+{ int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  uint64_t pf = keys[i] >> fshift;
+  /* sorted keys: equal prefixes are adjacent, so only the first of a run needs to set the bit */
+  if (i > 0 && (keys[i-1] >> fshift) == pf)
+    return;
+  atomicOr(filter + (pf>>5), 1u << (pf & 31));
+}
+
+extern "C" int hm_pick_filter_positions(int64_t n)
+{ int lg4 = 0;                                 /* ceil(log4 n) */
+  while (lg4 < 31 && ((int64_t) 1 << (2*lg4)) < n)
+    lg4 += 1;
+  int ph = lg4+2;                              /* ~1/16 .. 1/64 of the prefixes occupied */
+  if (ph < HM_FILTER_MIN_POS) ph = HM_FILTER_MIN_POS;
+  if (ph > HM_FILTER_MAX_POS) ph = HM_FILTER_MAX_POS;
+  return ph;
+}
+
+extern "C" int64_t hm_filter_words(int positions)
+{ return ((int64_t) 1 << (2*positions)) >> 5; }
+
+extern "C" int hm_k_build_filter(const uint64_t *d_keys, int64_t n, int positions,
+                                 uint32_t *d_filter, void *stream)
+{ if (positions < HM_FILTER_MIN_POS || positions > HM_FILTER_MAX_POS)
+    return hm_set_error(HM_EINVAL,"filter positions %d out of range %d..%d",positions,
+                        HM_FILTER_MIN_POS,HM_FILTER_MAX_POS);
+  HM_CUDA(cudaMemsetAsync(d_filter,0,sizeof(uint32_t)*(size_t) hm_filter_words(positions),
+                          (cudaStream_t) stream));
+  if (n <= 0)
+    return HM_OK;
+  int64_t nblk = (n+255)/256;
+  filter_build_kernel<<<(unsigned) nblk,256,0,(cudaStream_t) stream>>>(d_keys,n,64-2*positions,d_filter);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return hm_cuda_fail(e,"filter_build_kernel");
+  return HM_OK;
+}
+
 /* -------------------------------------------------------------------------- pass 1 ------ */
 
-/* One thread per table entry x = keys[i].  A neighbour y > x differing at base p shares x's
- * first p bases, and every entry between x and y in sorted order shares them too, so
- * p <= lcp(x, successor(x)): positions beyond that need no probe at all.  For the remaining
- * positions each larger base is tried by a prefix-bucket lookup + in-bucket bisection.  The
- * lower member of a pair does all the book-keeping: deg[x]+=1, deg[y]+=1 (byte-packed atomics),
- * up[x] = y.                                                                                 */
-template <typename IdxT>
-__global__ void __launch_bounds__(256)
-pass1_degree_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restrict__ cnt,
-                    int64_t n, const IdxT *__restrict__ bucket, int bshift, int kmer,
-                    int64_t lo, int64_t hi, uint32_t *__restrict__ deg32, IdxT *__restrict__ up)
-{ int64_t i = lo + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= hi)
-    return;
-  uint64_t x = keys[i];
-  int      pmax = -1;
-  if (i+1 < n)
-    { pmax = __clzll((long long) (x ^ keys[i+1])) >> 1;
-      if (pmax > kmer-1) pmax = kmer-1;
-    }
-  int      cx   = cnt[i];
-  unsigned udeg = 0;
-  IdxT     upj  = IdxNone<IdxT>::value;
+#define P1_WARPS   8            /* warps per CTA                                     */
+#define P1_QCAP    64           /* per-warp candidate queue: < 32 left + <= 32 pushed */
+#define P1_RUNCAP  12           /* forward scan bound for the high positions          */
 
-#pragma unroll 1
-  for (int p = 0; p <= pmax; p++)
-    { int sh = 62-2*p;
-      int b  = (int) ((x >> sh) & 3);
-      for (int d = 1; d <= 3-b; d++)
-        { uint64_t y = x + ((uint64_t) d << sh);
-          int64_t  j = bucket_find<IdxT>(keys,bucket,bshift,y);
-          if (j >= 0 && cx + (int) __ldg(cnt+j) <= HM_SMAX)
-            { udeg += 1;
-              upj   = (IdxT) j;
-              atomicAdd(deg32 + (j>>2), 1u << (8*(j&3)));
+/* book one qualifying pair (oi < j): both incidence bytes, and the upper partner of oi */
+template <typename IdxT>
+__device__ __forceinline__ void book_pair(const uint16_t *__restrict__ cnt, int64_t oi, int64_t j,
+                                          int64_t lo, uint32_t *__restrict__ deg32,
+                                          IdxT *__restrict__ up)
+{ if ((int) __ldg(cnt+oi) + (int) __ldg(cnt+j) <= HM_SMAX)         /* PloidyPlot.c:259 */
+    { atomicAdd(deg32 + (oi>>2), 1u << (8*(oi&3)));
+      atomicAdd(deg32 + (j>>2),  1u << (8*(j&3)));
+      up[oi-lo] = (IdxT) j;
+    }
+}
+
+/* A warp owns 32 consecutive table entries at a time (lane = entry).  For entry x only
+ * neighbours y > x are sought (the lower member books the pair), and a neighbour differing at
+ * base p shares x's first p bases with x AND with every entry between them, so p is bounded by
+ * lcp(x, successor(x)).
+ *
+ *   low positions  p < PH : y's 2*PH-bit prefix is tested against the presence filter -- one
+ *        predicated 4-byte load per (p, alt), fully unrolled, no divergence; survivors are only
+ *        remembered as bits of a per-lane mask.
+ *   high positions p >= PH: y shares x's filter prefix, so it sits in the short run of entries
+ *        that follow x with the same PH-base prefix: scan that run and test x^z for a
+ *        single-base difference (long runs fall back to per-position candidates).
+ *   survivors are expanded into a per-warp shared-memory queue and resolved 32 at a time by a
+ *        bucket lookup + bisection with every lane busy (the expensive, divergent part of the
+ *        search runs at full SIMT efficiency and only for ~1 candidate per entry).            */
+template <typename IdxT, int PH>
+__global__ void __launch_bounds__(P1_WARPS*32)
+pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restrict__ cnt,
+                    int64_t n, const IdxT *__restrict__ bucket, int bshift,
+                    const uint32_t *__restrict__ filter, int kmer,
+                    int64_t lo, int64_t hi, uint32_t *__restrict__ deg32, IdxT *__restrict__ up)
+{ __shared__ uint64_t s_qy[P1_WARPS][P1_QCAP];
+  __shared__ IdxT     s_qi[P1_WARPS][P1_QCAP];
+
+  const unsigned FULL = 0xffffffffu;
+  const int      lane = threadIdx.x & 31;
+  const int      warp = threadIdx.x >> 5;
+  const unsigned lt   = (1u << lane) - 1;
+  uint64_t *qy = s_qy[warp];
+  IdxT     *qi = s_qi[warp];
+  int       qn = 0;                                      /* warp-uniform queue fill */
+
+  const int64_t nchunks = (hi-lo+31) >> 5;
+  for (int64_t c = (int64_t) blockIdx.x * P1_WARPS + warp; c < nchunks;
+       c += (int64_t) gridDim.x * P1_WARPS)
+    { const int64_t i = lo + (c<<5) + lane;
+      const bool    valid = (i < hi);
+      uint64_t x = 0, nxt = 0;
+      int      pmax = -1;
+      if (valid)
+        { x = keys[i];
+          if (i+1 < n)
+            { nxt  = keys[i+1];
+              pmax = __clzll((long long) (x ^ nxt)) >> 1;
+              if (pmax > kmer-1) pmax = kmer-1;
+            }
+        }
+
+      /* ---- low positions: filter probes, branch-free ---- */
+      uint64_t mlo = 0;
+#pragma unroll
+      for (int p = 0; p < PH; p++)
+        { const int sh = 62-2*p;
+          const int b  = (int) ((x >> sh) & 3);
+#pragma unroll
+          for (int d = 1; d <= 3; d++)
+            { const bool     act = (p <= pmax) && (b+d <= 3);
+              const uint64_t pf  = (x + ((uint64_t) d << sh)) >> (64-2*PH);
+              uint32_t w = 0;
+              if (act)
+                w = __ldg(filter + (pf>>5));
+              if ((w >> (pf & 31)) & 1)
+                mlo |= (uint64_t) 1 << (3*p+d-1);
+            }
+        }
+
+      /* ---- high positions: the run of entries sharing x's PH-base prefix ---- */
+      uint64_t mhi = 0;
+      if (pmax >= PH)
+        { bool longrun = (i+P1_RUNCAP < n) &&
+                         (((x ^ __ldg(keys+i+P1_RUNCAP)) >> (64-2*PH)) == 0);
+          if (longrun)
+            { for (int p = PH; p <= pmax; p++)
+                { int b = (int) ((x >> (62-2*p)) & 3);
+                  for (int d = 1; d <= 3-b; d++)
+                    mhi |= (uint64_t) 1 << (3*(p-PH)+d-1);
+                }
+            }
+          else
+            { int64_t  j = i+1;
+              uint64_t z = nxt;
+              while (true)
+                { uint64_t dd = x ^ z;
+                  if ((dd >> (64-2*PH)) != 0)
+                    break;
+                  uint64_t t = (dd | (dd>>1)) & 0x5555555555555555ull;
+                  if ((t & (t-1)) == 0)                    /* exactly one base differs */
+                    book_pair<IdxT>(cnt,i,j,lo,deg32,up);
+                  j += 1;
+                  if (j >= n)
+                    break;
+                  z = __ldg(keys+j);
+                }
+            }
+        }
+
+      /* ---- expand survivors into the warp queue; resolve 32 at a time ---- */
+      while (__any_sync(FULL,(mlo | mhi) != 0))
+        { const bool has = (mlo | mhi) != 0;
+          uint64_t   y = 0;
+          if (has)
+            { int p, d;
+              if (mlo != 0)
+                { int t = __ffsll((long long) mlo)-1;
+                  mlo &= mlo-1;
+                  p = t/3; d = t-3*p+1;
+                }
+              else
+                { int t = __ffsll((long long) mhi)-1;
+                  mhi &= mhi-1;
+                  p = t/3; d = t-3*p+1; p += PH;
+                }
+              y = x + ((uint64_t) d << (62-2*p));
+            }
+          const unsigned bal = __ballot_sync(FULL,has);
+          if (has)
+            { int pos = qn + __popc(bal & lt);
+              qy[pos] = y;
+              qi[pos] = (IdxT) i;
+            }
+          qn += __popc(bal);
+          __syncwarp();
+          if (qn >= 32)
+            { qn -= 32;
+              uint64_t yy = qy[qn+lane];
+              int64_t  oi = (int64_t) qi[qn+lane];
+              __syncwarp();
+              int64_t j = bucket_find<IdxT>(keys,bucket,bshift,yy);
+              if (j >= 0)
+                book_pair<IdxT>(cnt,oi,j,lo,deg32,up);
             }
         }
     }
-  if (udeg != 0)
-    atomicAdd(deg32 + (i>>2), udeg << (8*(i&3)));
-  up[i-lo] = upj;
+
+  if (lane < qn)                                          /* left-overs */
+    { uint64_t yy = qy[lane];
+      int64_t  oi = (int64_t) qi[lane];
+      int64_t  j  = bucket_find<IdxT>(keys,bucket,bshift,yy);
+      if (j >= 0)
+        book_pair<IdxT>(cnt,oi,j,lo,deg32,up);
+    }
+}
+
+template <typename IdxT, int PH>
+static cudaError_t launch_pass1(const uint64_t *keys, const uint16_t *cnt, int64_t n,
+                                const void *bucket, int bits, const uint32_t *filter, int kmer,
+                                int64_t lo, int64_t hi, uint8_t *deg, void *up, cudaStream_t st)
+{ int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms,cudaDevAttrMultiProcessorCount,dev);
+  int64_t nchunks = (hi-lo+31)>>5;
+  int64_t want    = (nchunks+P1_WARPS-1)/P1_WARPS;
+  int64_t cap     = (int64_t) sms*8*4;            /* 4 waves of 8 resident CTAs per SM */
+  int     grid    = (int) (want < cap ? want : cap);
+  pass1_filter_kernel<IdxT,PH><<<grid,P1_WARPS*32,0,st>>>
+      (keys,cnt,n,(const IdxT *) bucket,64-bits,filter,kmer,lo,hi,(uint32_t *) deg,(IdxT *) up);
+  return cudaGetLastError();
+}
+
+template <typename IdxT>
+static cudaError_t dispatch_pass1(int ph, const uint64_t *keys, const uint16_t *cnt, int64_t n,
+                                  const void *bucket, int bits, const uint32_t *filter, int kmer,
+                                  int64_t lo, int64_t hi, uint8_t *deg, void *up, cudaStream_t st)
+{ switch (ph)
+  {
+#define CASE(P) case P: return launch_pass1<IdxT,P>(keys,cnt,n,bucket,bits,filter,kmer,lo,hi,deg,up,st);
+    CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16) CASE(17) CASE(18)
+#undef CASE
+  }
+  return cudaErrorInvalidValue;
 }
 
 extern "C" int hm_k_pass1_degree(const uint64_t *d_keys, const uint16_t *d_cnt, int64_t n,
-                                 const void *d_bucket, int bits, int idx64, int kmer,
+                                 const void *d_bucket, int bits, int idx64,
+                                 const uint32_t *d_filter, int filter_positions, int kmer,
                                  int64_t lo, int64_t hi, uint8_t *d_deg, void *d_up, void *stream)
 { if (kmer < 1 || kmer > HM_MAX_KMER)
     return hm_set_error(HM_EUNSUPPORTED,"k-mer length %d not supported (1..%d)",kmer,HM_MAX_KMER);
   if (lo < 0 || hi > n || lo > hi || bits < 1 || bits > 30)
     return hm_set_error(HM_EINVAL,"pass1: bad range [%lld,%lld) of %lld or bits %d",
                         (long long) lo,(long long) hi,(long long) n,bits);
+  if (filter_positions < HM_FILTER_MIN_POS || filter_positions > HM_FILTER_MAX_POS)
+    return hm_set_error(HM_EINVAL,"pass1: filter positions %d out of range",filter_positions);
   if (hi == lo)
     return HM_OK;
-  int64_t nblk = (hi-lo+255)/256;
-  if (idx64)
-    pass1_degree_kernel<uint64_t><<<(unsigned) nblk,256,0,(cudaStream_t) stream>>>
-        (d_keys,d_cnt,n,(const uint64_t *) d_bucket,64-bits,kmer,lo,hi,(uint32_t *) d_deg,(uint64_t *) d_up);
-  else
-    pass1_degree_kernel<uint32_t><<<(unsigned) nblk,256,0,(cudaStream_t) stream>>>
-        (d_keys,d_cnt,n,(const uint32_t *) d_bucket,64-bits,kmer,lo,hi,(uint32_t *) d_deg,(uint32_t *) d_up);
-  cudaError_t e = cudaGetLastError();
+  cudaStream_t st = (cudaStream_t) stream;
+  HM_CUDA(cudaMemsetAsync(d_up,0xFF,(idx64 ? 8 : 4)*(size_t) (hi-lo),st));   /* all-ones = none */
+  cudaError_t e = idx64
+      ? dispatch_pass1<uint64_t>(filter_positions,d_keys,d_cnt,n,d_bucket,bits,d_filter,kmer,lo,hi,d_deg,d_up,st)
+      : dispatch_pass1<uint32_t>(filter_positions,d_keys,d_cnt,n,d_bucket,bits,d_filter,kmer,lo,hi,d_deg,d_up,st);
   if (e != cudaSuccess)
-    return hm_cuda_fail(e,"pass1_degree_kernel");
+    return hm_cuda_fail(e,"pass1_filter_kernel");
   return HM_OK;
 }
 

@@ -33,13 +33,14 @@ typedef struct
     uint16_t           *cnt;
     uint8_t            *deg;          /* n rounded up to 4 */
     void               *bucket;
+    uint32_t           *filter;       /* prefix presence bitmap */
     void               *up;           /* hi-lo entries */
     unsigned long long *plot;
     int64_t             lo, hi;       /* this device's work range */
   } DevTable;
 
 struct hm_scan
-  { int      kmer, ibyte, bits, idx64, ngpu;
+  { int      kmer, ibyte, bits, fpos, idx64, ngpu;
     int64_t  n;
     DevTable d[HM_MAX_GPUS];
     double   ms_load;
@@ -64,6 +65,7 @@ static void free_dev(DevTable *D)
   if (D->cnt)    cudaFree(D->cnt);
   if (D->deg)    cudaFree(D->deg);
   if (D->bucket) cudaFree(D->bucket);
+  if (D->filter) cudaFree(D->filter);
   if (D->up)     cudaFree(D->up);
   if (D->plot)   cudaFree(D->plot);
   if (D->st)      cudaStreamDestroy(D->st);
@@ -148,6 +150,7 @@ extern "C" int hm_scan_create(const hm_host_table *t, const int *dev, int n_gpus
     return hm_set_error(HM_ENOMEM,"out of host memory");
   s->kmer = t->kmer; s->ibyte = t->ibyte; s->n = t->nels; s->ngpu = n_gpus;
   s->bits  = hm_pick_bucket_bits(s->n);
+  s->fpos  = hm_pick_filter_positions(s->n);
   s->idx64 = (s->n >= 0xFFFFFFF0ll);
   int64_t n  = s->n;
   size_t  ib = s->idx64 ? 8 : 4;
@@ -171,6 +174,7 @@ extern "C" int hm_scan_create(const hm_host_table *t, const int *dev, int n_gpus
       TRY(cudaMalloc(&D->cnt,sizeof(uint16_t)*(size_t) (n+1)));
       TRY(cudaMalloc(&D->deg,(size_t) ((n+4)&~3ll)));
       TRY(cudaMalloc(&D->bucket,ib*(((size_t) 1<<s->bits)+1)));
+      TRY(cudaMalloc(&D->filter,sizeof(uint32_t)*(size_t) hm_filter_words(s->fpos)));
       TRY(cudaMalloc(&D->up,ib*(size_t) (D->hi-D->lo+1)));
       TRY(cudaMalloc(&D->plot,sizeof(unsigned long long)*HM_PLOT_CELLS));
 #undef TRY
@@ -211,7 +215,9 @@ extern "C" int hm_scan_create(const hm_host_table *t, const int *dev, int n_gpus
     { DevTable *D = s->d+g;
       cudaSetDevice(D->dev);
       rc = hm_k_build_bucket_index(D->keys,n,s->bits,D->bucket,s->idx64,D->st);
-      s->launches += 1;
+      if (rc == HM_OK)
+        rc = hm_k_build_filter(D->keys,n,s->fpos,D->filter,D->st);
+      s->launches += 2;
     }
   for (int g = 0; g < n_gpus; g++)
     { cudaSetDevice(s->d[g].dev);
@@ -304,7 +310,7 @@ extern "C" int hm_scan_run(hm_scan *s, int64_t *plot, hm_scan_stats *stats)
       HM_CUDA(cudaEventRecord(ev[g][0],D->st));
       HM_CUDA(cudaMemsetAsync(D->deg,0,(size_t) ((n+4)&~3ll),D->st));
       HM_CUDA(cudaMemsetAsync(D->plot,0,sizeof(unsigned long long)*HM_PLOT_CELLS,D->st));
-      rc = hm_k_pass1_degree(D->keys,D->cnt,n,D->bucket,s->bits,s->idx64,s->kmer,
+      rc = hm_k_pass1_degree(D->keys,D->cnt,n,D->bucket,s->bits,s->idx64,D->filter,s->fpos,s->kmer,
                              D->lo,D->hi,D->deg,D->up,D->st);
       if (rc != HM_OK) return rc;
       s->launches += (D->hi > D->lo);
@@ -360,6 +366,7 @@ extern "C" int hm_scan_run(hm_scan *s, int64_t *plot, hm_scan_stats *stats)
     }
   if (stats != NULL)
     { stats->nels = n; stats->n_gpus = G; stats->bucket_bits = s->bits;
+      stats->filter_positions = s->fpos; stats->reserved = 0;
       stats->ms_h2d_unpack = s->ms_load;
       stats->ms_pass1 = ms1; stats->ms_pass2 = ms2;
       stats->ms_scan = G > 1 ? (t1-t0) : msall;

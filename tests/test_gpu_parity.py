@@ -136,18 +136,19 @@ def test_two_entry_and_pairless_tables(tmp_path):
 
 
 def test_result_independent_of_bucket_bits_and_work_split():
-    """layer A on torch tensors: any bucket width and any split of the index range into work
+    """layer A on torch tensors: any bucket width, any prefix-filter width and any split of the index range into work
     ranges (the multi-GPU sharding) gives the same plot."""
     import torch
     from smudgeplot_b200.device import DeviceTable
     keys, cnt = synth.synth_table(25, 60000, 3, 0.02, 60, 8, 77, device="cuda")
     c16 = cnt.to(torch.int16)
     ref = None
-    for bits in (2, 9, 15, 20):
-        t = DeviceTable(25, keys, c16, bits=bits).build_index()
+    for bits, fpos in ((2, 11), (9, 12), (15, 13), (20, 14), (17, 15), (17, 16), (12, 17), (17, 18)):
+        t = DeviceTable(25, keys, c16, bits=bits, fpos=fpos).build_index()
         p = t.scan().clone()
         ref = p if ref is None else ref
-        assert torch.equal(p, ref)
+        assert torch.equal(p, ref), (bits, fpos)
+        del t
     n = keys.numel()
     t = DeviceTable(25, keys, c16).build_index()
     cuts = [0, n // 7, n // 2, n - 3, n]
@@ -155,7 +156,7 @@ def test_result_independent_of_bucket_bits_and_work_split():
     parts = []
     for lo, hi in zip(cuts[:-1], cuts[1:]):
         w = DeviceTable(25, keys, c16)
-        w.bucket = t.bucket
+        w.bucket, w.filter = t.bucket, t.filter
         w.alloc_work(lo, hi)
         w.deg = deg                       # shared incidence array == result of the all-reduce
         w.pass1()
