@@ -5,7 +5,7 @@
 NVCC   ?= nvcc
 CC     ?= gcc
 ARCH   := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC,-Wall,-Wextra -Iinclude -Ismudgeplot_b200/csrc
+NVFLAGS := $(EXTRA) -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC,-Wall,-Wextra -Iinclude -Ismudgeplot_b200/csrc
 CFLAGS := -O2 -Wall -Wextra -fPIC -Iinclude -Ismudgeplot_b200/csrc
 
 LIBDIR := smudgeplot_b200/lib

@@ -208,7 +208,7 @@ extern "C" int hm_pick_filter_positions(int64_t n)
 { int lg4 = 0;                                 /* ceil(log4 n) */
   while (lg4 < 31 && ((int64_t) 1 << (2*lg4)) < n)
     lg4 += 1;
-  int ph = lg4+2;                              /* ~1/16 .. 1/64 of the prefixes occupied */
+  int ph = lg4+3;                              /* ~1/64 .. 1/256 of the prefixes occupied */
   if (ph < HM_FILTER_MIN_POS) ph = HM_FILTER_MIN_POS;
   if (ph > HM_FILTER_MAX_POS) ph = HM_FILTER_MAX_POS;
   return ph;
@@ -237,6 +237,9 @@ extern "C" int hm_k_build_filter(const uint64_t *d_keys, int64_t n, int position
 /* -------------------------------------------------------------------------- pass 1 ------ */
 
 #define P1_WARPS   8            /* warps per CTA                                     */
+#ifndef P1_MINBLOCKS
+#define P1_MINBLOCKS 6          /* resident CTAs per SM the register budget must allow (40 regs, no spills) */
+#endif
 #define P1_QCAP    64           /* per-warp candidate queue: < 32 left + <= 32 pushed */
 #define P1_RUNCAP  12           /* forward scan bound for the high positions          */
 
@@ -267,7 +270,7 @@ __device__ __forceinline__ void book_pair(const uint16_t *__restrict__ cnt, int6
  *        bucket lookup + bisection with every lane busy (the expensive, divergent part of the
  *        search runs at full SIMT efficiency and only for ~1 candidate per entry).            */
 template <typename IdxT, int PH>
-__global__ void __launch_bounds__(P1_WARPS*32)
+__global__ void __launch_bounds__(P1_WARPS*32,P1_MINBLOCKS)
 pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restrict__ cnt,
                     int64_t n, const IdxT *__restrict__ bucket, int bshift,
                     const uint32_t *__restrict__ filter, int kmer,
@@ -299,21 +302,47 @@ pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restric
             }
         }
 
-      /* ---- low positions: filter probes, branch-free ---- */
-      uint64_t mlo = 0;
+      /* ---- low positions: filter probes, branch-free ----
+       * candidate = x with base p replaced by c in {1,2,3}; it is wanted iff it is > x (c above
+       * the current base).  Survivor bits are shifted into two 32-bit masks in probe order:
+       * ma holds positions [0,NA), mb positions [NA,PH).                                       */
+      constexpr int NA  = PH < 9 ? PH : 9;
+      constexpr int SFT = 2*PH > 32 ? 2*PH-32 : 0;          /* filter bits taken from the low word */
+      const uint32_t xh = (uint32_t) (x >> 32), xl = (uint32_t) x;
+      uint32_t ma = 0, mb = 0;
 #pragma unroll
       for (int p = 0; p < PH; p++)
-        { const int sh = 62-2*p;
-          const int b  = (int) ((x >> sh) & 3);
+        { const bool pa = (p <= pmax);
 #pragma unroll
-          for (int d = 1; d <= 3; d++)
-            { const bool     act = (p <= pmax) && (b+d <= 3);
-              const uint64_t pf  = (x + ((uint64_t) d << sh)) >> (64-2*PH);
+          for (int c = 1; c <= 3; c++)
+            { bool     act;
+              uint32_t widx, bit;
+              if (p < 16)                                    /* base p lives in the high word */
+                { const int      s  = 30-2*p;
+                  const uint32_t yh = (xh & ~(3u << s)) | ((uint32_t) c << s);
+                  act = pa && (yh > xh);
+                  if (2*PH <= 32)
+                    { widx = yh >> (37-2*PH);
+                      bit  = (yh >> (32-2*PH)) & 31;
+                    }
+                  else
+                    { widx = yh >> (5-SFT);
+                      bit  = ((yh << SFT) | (xl >> (32-SFT))) & 31;
+                    }
+                }
+              else                                           /* PH > 16: base p in the low word */
+                { const int      s  = 62-2*p;
+                  const uint32_t yl = (xl & ~(3u << s)) | ((uint32_t) c << s);
+                  act  = pa && (yl > xl);
+                  widx = xh >> (5-SFT);
+                  bit  = ((xh << SFT) | (yl >> (32-SFT))) & 31;
+                }
               uint32_t w = 0;
               if (act)
-                w = __ldg(filter + (pf>>5));
-              if ((w >> (pf & 31)) & 1)
-                mlo |= (uint64_t) 1 << (3*p+d-1);
+                w = __ldg(filter + widx);
+              const uint32_t hit = (w >> bit) & 1;
+              if (p < NA) ma = (ma << 1) | hit;
+              else        mb = (mb << 1) | hit;
             }
         }
 
@@ -325,8 +354,8 @@ pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restric
           if (longrun)
             { for (int p = PH; p <= pmax; p++)
                 { int b = (int) ((x >> (62-2*p)) & 3);
-                  for (int d = 1; d <= 3-b; d++)
-                    mhi |= (uint64_t) 1 << (3*(p-PH)+d-1);
+                  for (int c = b+1; c <= 3; c++)
+                    mhi |= (uint64_t) 1 << (3*(p-PH)+c-1);
                 }
             }
           else
@@ -348,22 +377,30 @@ pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restric
         }
 
       /* ---- expand survivors into the warp queue; resolve 32 at a time ---- */
-      while (__any_sync(FULL,(mlo | mhi) != 0))
-        { const bool has = (mlo | mhi) != 0;
+      while (__any_sync(FULL,(ma | mb | mhi) != 0))
+        { const bool has = (ma | mb | mhi) != 0;
           uint64_t   y = 0;
           if (has)
-            { int p, d;
-              if (mlo != 0)
-                { int t = __ffsll((long long) mlo)-1;
-                  mlo &= mlo-1;
-                  p = t/3; d = t-3*p+1;
+            { int p, c;
+              if (ma != 0)
+                { int t = 31-__clz((int) ma);
+                  ma &= ~(1u << t);
+                  int q = 3*NA-1-t;
+                  p = q/3; c = q-3*p+1;
+                }
+              else if (mb != 0)
+                { int t = 31-__clz((int) mb);
+                  mb &= ~(1u << t);
+                  int q = 3*(PH-NA)-1-t;
+                  p = q/3; c = q-3*p+1; p += NA;
                 }
               else
                 { int t = __ffsll((long long) mhi)-1;
                   mhi &= mhi-1;
-                  p = t/3; d = t-3*p+1; p += PH;
+                  p = t/3; c = t-3*p+1; p += PH;
                 }
-              y = x + ((uint64_t) d << (62-2*p));
+              const int sh = 62-2*p;
+              y = (x & ~((uint64_t) 3 << sh)) | ((uint64_t) c << sh);
             }
           const unsigned bal = __ballot_sync(FULL,has);
           if (has)
@@ -448,15 +485,16 @@ extern "C" int hm_k_pass1_degree(const uint64_t *d_keys, const uint16_t *d_cnt, 
 
 /* -------------------------------------------------------------------------- pass 2 ------ */
 
-#define P2_TS 256      /* shared-memory tile: sums  < 256 */
-#define P2_TM 128      /*                     mins  < 128 */
-#define P2_THREADS 1024
+#define P2_TS 192      /* shared-memory tile: sums  < 192 */
+#define P2_TM 96       /*                     mins  <  96   (72 KB -> 3 CTAs per SM) */
+#define P2_THREADS 512
+#define P2_CTAS_PER_SM 3
 
 /* deg[x] <= 1 and deg[y] <= 1 for a recorded qualifying pair means both are exactly 1, i.e. the
  * pair is isolated: one count in plot[cx+cy][min].  Persistent CTAs keep the dense corner of the
  * plot in shared memory (uint32) and flush once; the rest goes to 64-bit global atomics.      */
 template <typename IdxT>
-__global__ void __launch_bounds__(P2_THREADS,1)
+__global__ void __launch_bounds__(P2_THREADS,P2_CTAS_PER_SM)
 pass2_plot_kernel(const uint16_t *__restrict__ cnt, const uint8_t *__restrict__ deg,
                   const IdxT *__restrict__ up, int64_t lo, int64_t hi,
                   unsigned long long *__restrict__ plot)
@@ -509,7 +547,7 @@ extern "C" int hm_k_pass2_plot(const uint16_t *d_cnt, const uint8_t *d_deg, cons
       configured[dev] = 1;
     }
   int64_t want = (hi-lo+P2_THREADS-1)/P2_THREADS;
-  int     grid = (int) (want < sms ? want : sms);
+  int     grid = (int) (want < sms*P2_CTAS_PER_SM ? want : sms*P2_CTAS_PER_SM);
   if (idx64)
     pass2_plot_kernel<uint64_t><<<grid,P2_THREADS,smem,(cudaStream_t) stream>>>
         (d_cnt,d_deg,(const uint64_t *) d_up,lo,hi,d_plot);
