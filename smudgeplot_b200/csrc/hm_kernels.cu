@@ -5,9 +5,10 @@
  * Integer / memory-bound work: no tensor cores (see DESIGN.md §5 for the roofline).
  *
  * What replaces what (reference file:line under /root/reference/src/lib):
- *   unpack_records_kernel   Next_Kmer_Entry + Current_Entry   libfastk.c:1159-1176,:1230-1269
+ *   unpack_records_{tma_,}kernel  Next_Kmer_Entry + Current_Entry   libfastk.c:1159-1176,:1230-1269
  *   bucket_index_kernel     stub index + GoTo_Kmer_Entry       libfastk.c:1320-1409
- *   pass1_degree_kernel     analysis_in_core_1 / _thread_1     PloidyPlot.c:454-568,:168-301
+ *   filter_build_kernel     (none: the merge's "no head has this suffix", PloidyPlot.c:618-643)
+ *   pass1_filter_kernel     analysis_in_core_1 / _thread_1     PloidyPlot.c:454-568,:168-301
  *   pass2_plot_kernel       analysis_in_core_2 / _thread_2     PloidyPlot.c:570-700,:303-452
  *   min_count_kernel        examine_table (trim half)          PloidyPlot.c:1171-1197
  *   find_keys_kernel        GoTo_Kmer_Entry exact-hit use      PloidyPlot.c:1213
@@ -130,6 +131,84 @@ unpack_records_kernel(const uint8_t *__restrict__ rec, int64_t n, int64_t first,
   cnt[i]  = (uint16_t) (r[hbyte] | (r[hbyte+1]<<8));
 }
 
+/* ---- TMA-staged variant ---------------------------------------------------------------
+ * FastK records are 5..9 bytes at an odd stride, so a thread-per-record global read is a string
+ * of byte loads.  Here one elected thread asks the TMA engine for the CTA's whole tile of
+ * UNP_TILE records (cp.async.bulk global -> shared, completion on an mbarrier; SASS: UBLKCP),
+ * the CTA narrows the stub-index range while the bytes are in flight, and the unaligned record
+ * fields are then picked out of shared memory; keys/counts leave as coalesced 8- / 2-byte stores.
+ * Needs a 16-byte aligned source (tile size UNP_TILE*pbyte is a multiple of 16 by construction). */
+#define UNP_TILE 1024
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{ return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory"); }
+
+__device__ __forceinline__ void fence_proxy_async_smem(void)
+{ asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+               :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{ asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory"); }
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{ unsigned ok;
+  do
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  while (!ok);
+}
+
+__global__ void __launch_bounds__(256)
+unpack_records_tma_kernel(const uint8_t *__restrict__ rec, int64_t first,
+                          const int64_t *__restrict__ index, int ixlen, int ibyte, int hbyte,
+                          uint64_t *__restrict__ keys, uint16_t *__restrict__ cnt)
+{ extern __shared__ __align__(128) uint8_t s_rec[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_blo, s_bhi;
+  const int      pbyte = hbyte+2;
+  const unsigned bytes = (unsigned) (UNP_TILE*pbyte);
+  const int64_t  t0    = (int64_t) blockIdx.x * UNP_TILE;
+
+  if (threadIdx.x == 0)
+    { mbar_init(&s_bar,1);
+      fence_proxy_async_smem();
+    }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    { mbar_arrive_expect_tx(&s_bar,bytes);
+      bulk_copy_g2s(s_rec,rec + t0*pbyte,bytes,&s_bar);
+      s_blo = upper_bound_index(index,0,ixlen-1,first+t0);              /* overlaps the copy */
+      s_bhi = upper_bound_index(index,s_blo,ixlen-1,first+t0+UNP_TILE-1);
+    }
+  __syncthreads();
+  mbar_wait(&s_bar,0);
+
+  const int blo = s_blo, bhi = s_bhi;
+#pragma unroll
+  for (int k = 0; k < UNP_TILE/256; k++)
+    { const int      r = threadIdx.x + 256*k;
+      const int64_t  i = t0+r;
+      const uint8_t *q = s_rec + r*pbyte;
+      uint64_t b = (uint64_t) upper_bound_index(index,blo,bhi,first+i);
+      uint64_t v = 0;
+      for (int j = 0; j < hbyte; j++)
+        v = (v<<8) | q[j];
+      uint64_t key = b << (64-8*ibyte);
+      if (hbyte > 0)
+        key |= v << (64-8*(ibyte+hbyte));
+      keys[i] = key;
+      cnt[i]  = (uint16_t) (q[hbyte] | (q[hbyte+1]<<8));
+    }
+}
+
 extern "C" int hm_k_unpack_records(const uint8_t *d_rec, int64_t n, int64_t first,
                                    const int64_t *d_stub_index, int ibyte, int kmer,
                                    uint64_t *d_keys, uint16_t *d_cnt, void *stream)
@@ -140,12 +219,26 @@ extern "C" int hm_k_unpack_records(const uint8_t *d_rec, int64_t n, int64_t firs
     return hm_set_error(HM_EFORMAT,"prefix bytes ibyte=%d invalid for k=%d",ibyte,kmer);
   if (n <= 0)
     return HM_OK;
-  int64_t nblk = (n+255)/256;
-  unpack_records_kernel<<<(unsigned) nblk,256,0,(cudaStream_t) stream>>>
-      (d_rec,n,first,d_stub_index,1<<(8*ibyte),ibyte,kbyte-ibyte,d_keys,d_cnt);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess)
-    return hm_cuda_fail(e,"unpack_records_kernel");
+  int     hbyte = kbyte-ibyte, pbyte = hbyte+2;
+  int64_t done  = 0;
+  if ((((uintptr_t) d_rec) & 15) == 0 && n >= UNP_TILE)         /* full tiles through the TMA path */
+    { int64_t ntiles = n/UNP_TILE;
+      unpack_records_tma_kernel<<<(unsigned) ntiles,256,(size_t) UNP_TILE*pbyte,(cudaStream_t) stream>>>
+          (d_rec,first,d_stub_index,1<<(8*ibyte),ibyte,hbyte,d_keys,d_cnt);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess)
+        return hm_cuda_fail(e,"unpack_records_tma_kernel");
+      done = ntiles*UNP_TILE;
+    }
+  if (done < n)                                                   /* tail / unaligned source */
+    { int64_t m = n-done;
+      int64_t nblk = (m+255)/256;
+      unpack_records_kernel<<<(unsigned) nblk,256,0,(cudaStream_t) stream>>>
+          (d_rec + done*pbyte,m,first+done,d_stub_index,1<<(8*ibyte),ibyte,hbyte,d_keys+done,d_cnt+done);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess)
+        return hm_cuda_fail(e,"unpack_records_kernel");
+    }
   return HM_OK;
 }
 
@@ -287,19 +380,31 @@ pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restric
   int       qn = 0;                                      /* warp-uniform queue fill */
 
   const int64_t nchunks = (hi-lo+31) >> 5;
-  for (int64_t c = (int64_t) blockIdx.x * P1_WARPS + warp; c < nchunks;
-       c += (int64_t) gridDim.x * P1_WARPS)
+  const int64_t cstep   = (int64_t) gridDim.x * P1_WARPS;
+  int64_t  c = (int64_t) blockIdx.x * P1_WARPS + warp;
+  /* software pipeline: the next chunk's keys are requested before this chunk is worked on */
+  uint64_t x_nx = 0, nxt_nx = 0;
+  { const int64_t i = lo + (c<<5) + lane;
+    if (c < nchunks && i < hi)
+      { x_nx = keys[i];
+        if (i+1 < n) nxt_nx = keys[i+1];
+      }
+  }
+  for ( ; c < nchunks; c += cstep)
     { const int64_t i = lo + (c<<5) + lane;
       const bool    valid = (i < hi);
-      uint64_t x = 0, nxt = 0;
-      int      pmax = -1;
-      if (valid)
-        { x = keys[i];
-          if (i+1 < n)
-            { nxt  = keys[i+1];
-              pmax = __clzll((long long) (x ^ nxt)) >> 1;
-              if (pmax > kmer-1) pmax = kmer-1;
-            }
+      const uint64_t x = x_nx, nxt = nxt_nx;
+      { const int64_t i2 = i + (cstep<<5);
+        x_nx = 0; nxt_nx = 0;
+        if (c+cstep < nchunks && i2 < hi)
+          { x_nx = __ldg(keys+i2);
+            if (i2+1 < n) nxt_nx = __ldg(keys+i2+1);
+          }
+      }
+      int pmax = -1;
+      if (valid && i+1 < n)
+        { pmax = __clzll((long long) (x ^ nxt)) >> 1;
+          if (pmax > kmer-1) pmax = kmer-1;
         }
 
       /* ---- low positions: filter probes, branch-free ----
