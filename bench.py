@@ -308,7 +308,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": workload_name(world), "k": K, "ploidy": PLOIDY, "het": HET, "cov": COV, "L": LCUT,
                        "nels": nels, "nels_per_gpu": my_n, "seed": SEED, "bucket_bits": (job.bits if multi else table.bits),
-                       "filter_positions": (job.table.fpos if multi else table.fpos),
+                       "filter_bits": (job.table.fbits if multi else table.fbits),
                        "parallelism": f"table replica per GPU, {world} contiguous index shards" if multi else "1 GPU",
                        "l2": "inputs (>=1.9 GB table + bucket index per GPU) exceed the 126 MB L2; no flush between iterations"},
             "clocks": clk.summary(), "gpu_launches": launches,

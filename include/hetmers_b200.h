@@ -35,8 +35,8 @@ extern "C" {
 #define HM_PLOT_W      (HM_FMAX+1)
 #define HM_PLOT_CELLS  ((HM_SMAX+1)*(HM_FMAX+1))   /* int64 plot[1001][501] (PloidyPlot.c:1466-1473) */
 #define HM_MAX_KMER      32                 /* one 64-bit word per packed k-mer (this round) */
-#define HM_FILTER_MIN_POS 11                /* prefix-filter width in bases: 2*pos bits     */
-#define HM_FILTER_MAX_POS 18
+#define HM_FILTER_MIN_BITS 22               /* prefix-filter width in bits                  */
+#define HM_FILTER_MAX_BITS 37
 
 #define HM_OK            0
 #define HM_EINVAL       -1                  /* bad argument                                   */
@@ -77,14 +77,14 @@ int hm_k_unpack_records(const uint8_t *d_rec, int64_t n, int64_t first,
 int hm_k_build_bucket_index(const uint64_t *d_keys, int64_t n, int bits,
                             void *d_bucket, int idx64, void *stream);
 
-/* Prefix presence filter: bit f of d_filter is set iff some key starts with the 2*positions-bit
- * prefix f; hm_filter_words(positions) uint32 words (zeroed here).  It answers "is there any
+/* Prefix presence filter: bit f of d_filter is set iff some key starts with the filter_bits-bit
+ * prefix f; hm_filter_words(filter_bits) uint32 words (zeroed here).  It answers "is there any
  * k-mer with this prefix" for pass 1's probes -- the role the 4-way merge's "no list head has
  * this suffix" plays in the reference (PloidyPlot.c:618-643).                                  */
-int     hm_k_build_filter(const uint64_t *d_keys, int64_t n, int positions,
+int     hm_k_build_filter(const uint64_t *d_keys, int64_t n, int filter_bits,
                           uint32_t *d_filter, void *stream);
-int64_t hm_filter_words(int positions);
-int     hm_pick_filter_positions(int64_t n);
+int64_t hm_filter_words(int filter_bits);
+int     hm_pick_filter_bits(int64_t n);
 
 /* Pass 1 (PASS1=1 of PloidyPlot.c:1489; analysis_in_core_1 :454-568, analysis_thread_1
  * :168-301, big_window :712-842): for every entry x in [lo,hi) find every one-substitution
@@ -94,7 +94,7 @@ int     hm_pick_filter_positions(int64_t n);
  * first call (several ranges / GPUs accumulate into it).                                      */
 int hm_k_pass1_degree(const uint64_t *d_keys, const uint16_t *d_cnt, int64_t n,
                       const void *d_bucket, int bits, int idx64,
-                      const uint32_t *d_filter, int filter_positions, int kmer,
+                      const uint32_t *d_filter, int filter_bits, int kmer,
                       int64_t lo, int64_t hi, uint8_t *d_deg, void *d_up, void *stream);
 
 /* Pass 2 (PASS1=0; analysis_in_core_2 :570-700, analysis_thread_2 :303-452): for x in [lo,hi)
@@ -132,7 +132,7 @@ typedef struct hm_scan_stats
   { int64_t nels;
     int32_t n_gpus;
     int32_t bucket_bits;
-    int32_t filter_positions;
+    int32_t filter_bits;
     int32_t reserved;
     double  ms_h2d_unpack;       /* H2D copies + unpack + bucket index (T_load, device part) */
     double  ms_pass1;

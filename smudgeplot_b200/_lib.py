@@ -19,7 +19,7 @@ ABI_SYMBOLS = [
     "hm_last_error", "hm_abi_version", "hm_device_count", "hm_device_info",
     "hm_k_unpack_records", "hm_k_build_bucket_index", "hm_k_pass1_degree", "hm_k_pass2_plot",
     "hm_k_min_count", "hm_k_find_keys", "hm_pick_bucket_bits",
-    "hm_k_build_filter", "hm_filter_words", "hm_pick_filter_positions",
+    "hm_k_build_filter", "hm_filter_words", "hm_pick_filter_bits",
     "hm_scan_create", "hm_scan_destroy", "hm_scan_examine", "hm_scan_run", "hm_hetmers_host",
     "hm_scan_download", "hm_table_open", "hm_table_close", "hm_table_view", "hm_write_smu",
 ]
@@ -33,7 +33,7 @@ class HostTable(C.Structure):
 
 class ScanStats(C.Structure):
     _fields_ = [("nels", C.c_int64), ("n_gpus", C.c_int32), ("bucket_bits", C.c_int32),
-                ("filter_positions", C.c_int32), ("reserved", C.c_int32),
+                ("filter_bits", C.c_int32), ("reserved", C.c_int32),
                 ("ms_h2d_unpack", C.c_double), ("ms_pass1", C.c_double), ("ms_pass2", C.c_double),
                 ("ms_scan", C.c_double), ("ms_total", C.c_double), ("kernel_launches", C.c_int64)]
 
@@ -68,7 +68,7 @@ def lib():
     L.hm_k_build_filter.argtypes = [vp, i64, i32, vp, vp]
     L.hm_filter_words.argtypes = [i32]
     L.hm_filter_words.restype = i64
-    L.hm_pick_filter_positions.argtypes = [i64]
+    L.hm_pick_filter_bits.argtypes = [i64]
     L.hm_k_pass2_plot.argtypes = [vp, vp, vp, i32, i64, i64, vp, vp]
     L.hm_k_min_count.argtypes = [vp, i64, i64, vp, vp]
     L.hm_k_find_keys.argtypes = [vp, i64, vp, i32, i32, vp, i64, vp, vp]

@@ -280,8 +280,8 @@ extern "C" int hm_k_build_bucket_index(const uint64_t *d_keys, int64_t n, int bi
 
 /* ------------------------------------------------------------------ prefix filter ------- */
 
-/* Presence bitmap over the first 2*PH bits (PH bases) of every key: bit f set iff some table
- * entry starts with f.  ~16 bits per entry: a probe for a k-mer that is NOT in
+/* Presence bitmap over the first F bits of every key: bit f set iff some table entry starts
+ * with f.  64..128 bits per entry: a probe for a k-mer that is NOT in
  * the table -- 99 % of all probes -- is answered by one 4-byte load that neighbouring lanes
  * share, instead of a bucket lookup + bisection.                                              */
 __global__ void __launch_bounds__(256)
@@ -297,30 +297,35 @@ filter_build_kernel(const uint64_t *__restrict__ keys, int64_t n, int fshift,
   atomicOr(filter + (pf>>5), 1u << (pf & 31));
 }
 
-extern "C" int hm_pick_filter_positions(int64_t n)
-{ int lg4 = 0;                                 /* ceil(log4 n) */
-  while (lg4 < 31 && ((int64_t) 1 << (2*lg4)) < n)
-    lg4 += 1;
-  int ph = lg4+3;                              /* ~1/64 .. 1/256 of the prefixes occupied */
-  if (ph < HM_FILTER_MIN_POS) ph = HM_FILTER_MIN_POS;
-  if (ph > HM_FILTER_MAX_POS) ph = HM_FILTER_MAX_POS;
-  return ph;
+extern "C" int hm_pick_filter_bits(int64_t n)
+{ /* 45..90 filter bits per entry: measured optimum at 2e8 entries is 43..86 (7.6-8.0 ms), 21 costs
+   * +11 % (more survivors), 172 costs +50 % (filter traffic = #probed (position, base) pairs x
+   * filter size: every probe column streams the whole bitmap once)                              */
+  int lg = 0;                                  /* round(log2 n) */
+  while (lg < 62 && ((int64_t) 1 << (lg+1)) <= n)
+    lg += 1;
+  if (lg < 61 && (double) n > 1.41421356 * (double) ((int64_t) 1 << lg))
+    lg += 1;
+  int fb = lg+6;
+  if (fb < HM_FILTER_MIN_BITS) fb = HM_FILTER_MIN_BITS;
+  if (fb > HM_FILTER_MAX_BITS) fb = HM_FILTER_MAX_BITS;
+  return fb;
 }
 
-extern "C" int64_t hm_filter_words(int positions)
-{ return ((int64_t) 1 << (2*positions)) >> 5; }
+extern "C" int64_t hm_filter_words(int filter_bits)
+{ return ((int64_t) 1 << filter_bits) >> 5; }
 
-extern "C" int hm_k_build_filter(const uint64_t *d_keys, int64_t n, int positions,
+extern "C" int hm_k_build_filter(const uint64_t *d_keys, int64_t n, int filter_bits,
                                  uint32_t *d_filter, void *stream)
-{ if (positions < HM_FILTER_MIN_POS || positions > HM_FILTER_MAX_POS)
-    return hm_set_error(HM_EINVAL,"filter positions %d out of range %d..%d",positions,
-                        HM_FILTER_MIN_POS,HM_FILTER_MAX_POS);
-  HM_CUDA(cudaMemsetAsync(d_filter,0,sizeof(uint32_t)*(size_t) hm_filter_words(positions),
+{ if (filter_bits < HM_FILTER_MIN_BITS || filter_bits > HM_FILTER_MAX_BITS)
+    return hm_set_error(HM_EINVAL,"filter bits %d out of range %d..%d",filter_bits,
+                        HM_FILTER_MIN_BITS,HM_FILTER_MAX_BITS);
+  HM_CUDA(cudaMemsetAsync(d_filter,0,sizeof(uint32_t)*(size_t) hm_filter_words(filter_bits),
                           (cudaStream_t) stream));
   if (n <= 0)
     return HM_OK;
   int64_t nblk = (n+255)/256;
-  filter_build_kernel<<<(unsigned) nblk,256,0,(cudaStream_t) stream>>>(d_keys,n,64-2*positions,d_filter);
+  filter_build_kernel<<<(unsigned) nblk,256,0,(cudaStream_t) stream>>>(d_keys,n,64-filter_bits,d_filter);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return hm_cuda_fail(e,"filter_build_kernel");
@@ -353,7 +358,7 @@ __device__ __forceinline__ void book_pair(const uint16_t *__restrict__ cnt, int6
  * base p shares x's first p bases with x AND with every entry between them, so p is bounded by
  * lcp(x, successor(x)).
  *
- *   low positions  p < PH : y's 2*PH-bit prefix is tested against the presence filter -- one
+ *   low positions  p < PH = ceil(F/2): y's F-bit prefix is tested against the presence filter -- one
  *        predicated 4-byte load per (p, alt), fully unrolled, no divergence; survivors are only
  *        remembered as bits of a per-lane mask.
  *   high positions p >= PH: y shares x's filter prefix, so it sits in the short run of entries
@@ -362,7 +367,7 @@ __device__ __forceinline__ void book_pair(const uint16_t *__restrict__ cnt, int6
  *   survivors are expanded into a per-warp shared-memory queue and resolved 32 at a time by a
  *        bucket lookup + bisection with every lane busy (the expensive, divergent part of the
  *        search runs at full SIMT efficiency and only for ~1 candidate per entry).            */
-template <typename IdxT, int PH>
+template <typename IdxT, int F>
 __global__ void __launch_bounds__(P1_WARPS*32,P1_MINBLOCKS)
 pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restrict__ cnt,
                     int64_t n, const IdxT *__restrict__ bucket, int bshift,
@@ -371,6 +376,9 @@ pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restric
 { __shared__ uint64_t s_qy[P1_WARPS][P1_QCAP];
   __shared__ IdxT     s_qi[P1_WARPS][P1_QCAP];
 
+  constexpr int PH  = (F+1)/2;                              /* positions with a bit in the prefix */
+  constexpr int NA  = PH < 9 ? PH : 9;
+  constexpr int SFT = F > 32 ? F-32 : 0;                    /* filter bits taken from the low word */
   const unsigned FULL = 0xffffffffu;
   const int      lane = threadIdx.x & 31;
   const int      warp = threadIdx.x >> 5;
@@ -400,8 +408,6 @@ pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restric
        * candidate = x with base p replaced by c in {1,2,3}; it is wanted iff it is > x (c above
        * the current base).  Survivor bits are shifted into two 32-bit masks in probe order:
        * ma holds positions [0,NA), mb positions [NA,PH).                                       */
-      constexpr int NA  = PH < 9 ? PH : 9;
-      constexpr int SFT = 2*PH > 32 ? 2*PH-32 : 0;          /* filter bits taken from the low word */
       const uint32_t xh = (uint32_t) (x >> 32), xl = (uint32_t) x;
       uint32_t ma = 0, mb = 0;
 #pragma unroll
@@ -415,16 +421,16 @@ pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restric
                 { const int      s  = 30-2*p;
                   const uint32_t yh = (xh & ~(3u << s)) | ((uint32_t) c << s);
                   act = pa && (yh > xh);
-                  if (2*PH <= 32)
-                    { widx = yh >> (37-2*PH);
-                      bit  = (yh >> (32-2*PH)) & 31;
+                  if (F <= 32)
+                    { widx = yh >> (37-F);
+                      bit  = (yh >> (32-F)) & 31;
                     }
                   else
                     { widx = yh >> (5-SFT);
                       bit  = ((yh << SFT) | (xl >> (32-SFT))) & 31;
                     }
                 }
-              else                                           /* PH > 16: base p in the low word */
+              else                                           /* F > 32: base p in the low word */
                 { const int      s  = 62-2*p;
                   const uint32_t yl = (xl & ~(3u << s)) | ((uint32_t) c << s);
                   act  = pa && (yl > xl);
@@ -525,7 +531,7 @@ pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restric
     }
 }
 
-template <typename IdxT, int PH>
+template <typename IdxT, int F>
 static cudaError_t launch_pass1(const uint64_t *keys, const uint16_t *cnt, int64_t n,
                                 const void *bucket, int bits, const uint32_t *filter, int kmer,
                                 int64_t lo, int64_t hi, uint8_t *deg, void *up, cudaStream_t st)
@@ -536,19 +542,20 @@ static cudaError_t launch_pass1(const uint64_t *keys, const uint16_t *cnt, int64
   int64_t want    = (nchunks+P1_WARPS-1)/P1_WARPS;
   int64_t cap     = (int64_t) sms*8*4;            /* 4 waves of 8 resident CTAs per SM */
   int     grid    = (int) (want < cap ? want : cap);
-  pass1_filter_kernel<IdxT,PH><<<grid,P1_WARPS*32,0,st>>>
+  pass1_filter_kernel<IdxT,F><<<grid,P1_WARPS*32,0,st>>>
       (keys,cnt,n,(const IdxT *) bucket,64-bits,filter,kmer,lo,hi,(uint32_t *) deg,(IdxT *) up);
   return cudaGetLastError();
 }
 
 template <typename IdxT>
-static cudaError_t dispatch_pass1(int ph, const uint64_t *keys, const uint16_t *cnt, int64_t n,
+static cudaError_t dispatch_pass1(int fb, const uint64_t *keys, const uint16_t *cnt, int64_t n,
                                   const void *bucket, int bits, const uint32_t *filter, int kmer,
                                   int64_t lo, int64_t hi, uint8_t *deg, void *up, cudaStream_t st)
-{ switch (ph)
+{ switch (fb)
   {
 #define CASE(P) case P: return launch_pass1<IdxT,P>(keys,cnt,n,bucket,bits,filter,kmer,lo,hi,deg,up,st);
-    CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16) CASE(17) CASE(18)
+    CASE(22) CASE(23) CASE(24) CASE(25) CASE(26) CASE(27) CASE(28) CASE(29)
+    CASE(30) CASE(31) CASE(32) CASE(33) CASE(34) CASE(35) CASE(36) CASE(37)
 #undef CASE
   }
   return cudaErrorInvalidValue;
@@ -556,22 +563,22 @@ static cudaError_t dispatch_pass1(int ph, const uint64_t *keys, const uint16_t *
 
 extern "C" int hm_k_pass1_degree(const uint64_t *d_keys, const uint16_t *d_cnt, int64_t n,
                                  const void *d_bucket, int bits, int idx64,
-                                 const uint32_t *d_filter, int filter_positions, int kmer,
+                                 const uint32_t *d_filter, int filter_bits, int kmer,
                                  int64_t lo, int64_t hi, uint8_t *d_deg, void *d_up, void *stream)
 { if (kmer < 1 || kmer > HM_MAX_KMER)
     return hm_set_error(HM_EUNSUPPORTED,"k-mer length %d not supported (1..%d)",kmer,HM_MAX_KMER);
   if (lo < 0 || hi > n || lo > hi || bits < 1 || bits > 30)
     return hm_set_error(HM_EINVAL,"pass1: bad range [%lld,%lld) of %lld or bits %d",
                         (long long) lo,(long long) hi,(long long) n,bits);
-  if (filter_positions < HM_FILTER_MIN_POS || filter_positions > HM_FILTER_MAX_POS)
-    return hm_set_error(HM_EINVAL,"pass1: filter positions %d out of range",filter_positions);
+  if (filter_bits < HM_FILTER_MIN_BITS || filter_bits > HM_FILTER_MAX_BITS)
+    return hm_set_error(HM_EINVAL,"pass1: filter bits %d out of range",filter_bits);
   if (hi == lo)
     return HM_OK;
   cudaStream_t st = (cudaStream_t) stream;
   HM_CUDA(cudaMemsetAsync(d_up,0xFF,(idx64 ? 8 : 4)*(size_t) (hi-lo),st));   /* all-ones = none */
   cudaError_t e = idx64
-      ? dispatch_pass1<uint64_t>(filter_positions,d_keys,d_cnt,n,d_bucket,bits,d_filter,kmer,lo,hi,d_deg,d_up,st)
-      : dispatch_pass1<uint32_t>(filter_positions,d_keys,d_cnt,n,d_bucket,bits,d_filter,kmer,lo,hi,d_deg,d_up,st);
+      ? dispatch_pass1<uint64_t>(filter_bits,d_keys,d_cnt,n,d_bucket,bits,d_filter,kmer,lo,hi,d_deg,d_up,st)
+      : dispatch_pass1<uint32_t>(filter_bits,d_keys,d_cnt,n,d_bucket,bits,d_filter,kmer,lo,hi,d_deg,d_up,st);
   if (e != cudaSuccess)
     return hm_cuda_fail(e,"pass1_filter_kernel");
   return HM_OK;

@@ -150,7 +150,7 @@ extern "C" int hm_scan_create(const hm_host_table *t, const int *dev, int n_gpus
     return hm_set_error(HM_ENOMEM,"out of host memory");
   s->kmer = t->kmer; s->ibyte = t->ibyte; s->n = t->nels; s->ngpu = n_gpus;
   s->bits  = hm_pick_bucket_bits(s->n);
-  s->fpos  = hm_pick_filter_positions(s->n);
+  s->fpos  = hm_pick_filter_bits(s->n);
   s->idx64 = (s->n >= 0xFFFFFFF0ll);
   int64_t n  = s->n;
   size_t  ib = s->idx64 ? 8 : 4;
@@ -366,7 +366,7 @@ extern "C" int hm_scan_run(hm_scan *s, int64_t *plot, hm_scan_stats *stats)
     }
   if (stats != NULL)
     { stats->nels = n; stats->n_gpus = G; stats->bucket_bits = s->bits;
-      stats->filter_positions = s->fpos; stats->reserved = 0;
+      stats->filter_bits = s->fpos; stats->reserved = 0;
       stats->ms_h2d_unpack = s->ms_load;
       stats->ms_pass1 = ms1; stats->ms_pass2 = ms2;
       stats->ms_scan = G > 1 ? (t1-t0) : msall;

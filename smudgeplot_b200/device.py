@@ -6,7 +6,7 @@ only), every computation is one of our CUDA kernels in libhetmers_b200.so.
     cnt   int16[n]   (bit pattern of the uint16 count)
     deg   uint8[n+]  (the reference's `Pair` incidence array, PloidyPlot.c:163)
     bucket int32/int64[(1<<bits)+1]
-    filter int32[2^(2*fpos)/32]  (prefix presence bitmap probed by pass 1)
+    filter int32[2^fbits/32]  (prefix presence bitmap probed by pass 1)
     up    int32/int64[hi-lo]  (upper partner recorded by pass 1)
     plot  int64[1001*501]
 """
@@ -27,7 +27,7 @@ def _stream():
 
 class DeviceTable:
     def __init__(self, kmer: int, keys: torch.Tensor, cnt: torch.Tensor, bits: int | None = None,
-                 fpos: int | None = None):
+                 fbits: int | None = None):
         assert keys.is_cuda and keys.dtype == torch.int64 and keys.is_contiguous()
         assert cnt.is_cuda and cnt.dtype == torch.int16 and cnt.is_contiguous()
         self.L = _lib.lib()
@@ -38,7 +38,7 @@ class DeviceTable:
         self.idx64 = int(self.n >= 0xFFFFFFF0)
         self.idx_dtype = torch.int64 if self.idx64 else torch.int32
         self.bits = bits if bits is not None else self.L.hm_pick_bucket_bits(self.n)
-        self.fpos = fpos if fpos is not None else self.L.hm_pick_filter_positions(self.n)
+        self.fbits = fbits if fbits is not None else self.L.hm_pick_filter_bits(self.n)
         self.bucket = None
         self.filter = None
         self.deg = None
@@ -78,9 +78,9 @@ class DeviceTable:
         with torch.cuda.device(self.device):
             _lib.check(self.L.hm_k_build_bucket_index(_ptr(self.keys), self.n, self.bits,
                                                       _ptr(self.bucket), self.idx64, _stream()))
-        self.filter = torch.empty(self.L.hm_filter_words(self.fpos), dtype=torch.int32, device=self.device)
+        self.filter = torch.empty(self.L.hm_filter_words(self.fbits), dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self.L.hm_k_build_filter(_ptr(self.keys), self.n, self.fpos, _ptr(self.filter), _stream()))
+            _lib.check(self.L.hm_k_build_filter(_ptr(self.keys), self.n, self.fbits, _ptr(self.filter), _stream()))
         self.launches += 2
         return self
 
@@ -97,7 +97,7 @@ class DeviceTable:
         """neighbour search + degree (hm_k_pass1_degree) over [lo,hi); deg must be zero."""
         with torch.cuda.device(self.device):
             _lib.check(self.L.hm_k_pass1_degree(_ptr(self.keys), _ptr(self.cnt), self.n, _ptr(self.bucket),
-                                                self.bits, self.idx64, _ptr(self.filter), self.fpos, self.kmer,
+                                                self.bits, self.idx64, _ptr(self.filter), self.fbits, self.kmer,
                                                 self.lo, self.hi,
                                                 _ptr(self.deg), _ptr(self.up), _stream()))
         self.launches += 1

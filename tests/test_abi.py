@@ -23,8 +23,9 @@ def test_library_loads_and_exports_header_symbols(built):
     assert L.hm_abi_version() == 1
     assert L.hm_pick_bucket_bits(200_000_000) == 26
     assert L.hm_pick_bucket_bits(1) == 2
-    assert L.hm_pick_filter_positions(200_000_000) == 17 and L.hm_pick_filter_positions(2) == 11
-    assert L.hm_pick_filter_positions(5_000_000_000) == 18 and L.hm_filter_words(16) == (1 << 32) // 32
+    assert L.hm_pick_filter_bits(200_000_000) == 34 and L.hm_pick_filter_bits(2) == 22
+    assert L.hm_pick_filter_bits(400_000_000) == 35 and L.hm_pick_filter_bits(370_000_000) == 34 and L.hm_pick_filter_bits(5_000_000_000) == 37
+    assert L.hm_filter_words(32) == (1 << 32) // 32
 
 
 def run(*args, stdin="n\n"):

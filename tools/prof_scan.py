@@ -25,11 +25,11 @@ def main():
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--bits", type=int, default=None)
-    ap.add_argument("--fpos", type=int, default=None)
+    ap.add_argument("--fbits", type=int, default=None)
     a = ap.parse_args()
     G = synth.calibrate_G(a.k, int(a.nels), a.ploidy, a.het, a.cov, a.L)
     keys, cnt = synth.synth_table(a.k, G, a.ploidy, a.het, a.cov, a.L, a.seed, device="cuda")
-    t = DeviceTable(a.k, keys, cnt.to(torch.int16), bits=a.bits, fpos=a.fpos).build_index()
+    t = DeviceTable(a.k, keys, cnt.to(torch.int16), bits=a.bits, fbits=a.fbits).build_index()
     t.alloc_work()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     for it in range(a.iters):
@@ -41,7 +41,7 @@ def main():
         t.pass2()
         ev[2].record()
         torch.cuda.synchronize()
-        print(f"iter {it}: n={t.n} bits={t.bits} fpos={t.fpos} pass1 {ev[0].elapsed_time(ev[1]):.3f} ms  "
+        print(f"iter {it}: n={t.n} bits={t.bits} fbits={t.fbits} pass1 {ev[0].elapsed_time(ev[1]):.3f} ms  "
               f"pass2 {ev[1].elapsed_time(ev[2]):.3f} ms  pairs {int(t.plot.sum())}", flush=True)
 
 
