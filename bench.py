@@ -157,8 +157,9 @@ def time_reference(table, nels, threads, runs=1):
 
 
 def cpu_sample_size(args, threads):
-    # survey anchor: ~0.45e6 k-mers/s per thread at k=31; bounded by the GPU workload
-    n = 0.45e6 * threads * args.cpu_seconds
+    # survey anchor ~0.45e6 k-mers/s per thread at k=31, but the reference stops scaling
+    # near 8-9e6 k-mers/s (measured: 8.4e6/s at -T64 on the 128-core B200 host); bounded by the GPU workload
+    n = min(0.45e6 * threads, 9e6) * args.cpu_seconds
     return int(max(2e6, min(n, args.nels)))
 
 
