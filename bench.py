@@ -310,7 +310,7 @@ def run_ours(args):
             "config": {"workload": workload_name(world), "k": K, "ploidy": PLOIDY, "het": HET, "cov": COV, "L": LCUT,
                        "nels": nels, "nels_per_gpu": my_n, "seed": SEED, "bucket_bits": (job.bits if multi else table.bits),
                        "filter_bits": (job.table.fbits if multi else table.fbits),
-                       "parallelism": f"table replica per GPU, {world} contiguous index shards" if multi else "1 GPU",
+                       "parallelism": f"table replica per GPU, {world} contiguous index shards; degree exchange: {job.exchange}" if multi else "1 GPU",
                        "l2": "inputs (>=1.9 GB table + bucket index per GPU) exceed the 126 MB L2; no flush between iterations"},
             "clocks": clk.summary(), "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "pass1_filter_kernel", "achieved": achieved, "peak": peak,

@@ -35,6 +35,7 @@ extern "C" {
 #define HM_PLOT_W      (HM_FMAX+1)
 #define HM_PLOT_CELLS  ((HM_SMAX+1)*(HM_FMAX+1))   /* int64 plot[1001][501] (PloidyPlot.c:1466-1473) */
 #define HM_MAX_KMER      32                 /* one 64-bit word per packed k-mer (this round) */
+#define HM_MAX_SHARDS    16                 /* GPUs one table can be sharded over           */
 #define HM_FILTER_MIN_BITS 22               /* prefix-filter width in bits                  */
 #define HM_FILTER_MAX_BITS 37
 
@@ -86,6 +87,21 @@ int     hm_k_build_filter(const uint64_t *d_keys, int64_t n, int filter_bits,
 int64_t hm_filter_words(int filter_bits);
 int     hm_pick_filter_bits(int64_t n);
 
+/* Sharded incidence array (multi-GPU).  The table is cut into n_shards contiguous
+ * index ranges [off[r], off[r+1]); GPU r owns the incidence bytes of shard r.  deg[r] is GPU r's
+ * FULL-LENGTH array as addressable from the calling GPU (peer access in one process, or a CUDA
+ * IPC mapping from hm_ipc_open between processes); only its slice r is meaningful.  With such a
+ * table pass 1 adds to a foreign partner's byte with a remote atomic over NVLink and pass 2 reads
+ * a foreign partner's byte with a remote load, so no collective has to move the array; the caller
+ * only orders the phases (all pass 1 kernels done -> pass 2; all pass 2 done -> next zeroing).
+ * NULL (or n_shards <= 1) = dense mode: every byte lives in d_deg.                              */
+typedef struct hm_shards
+  { int32_t  n_shards;
+    int32_t  self;                          /* the calling GPU's shard                          */
+    int64_t  off[HM_MAX_SHARDS+1];
+    uint8_t *deg[HM_MAX_SHARDS];
+  } hm_shards;
+
 /* Pass 1 (PASS1=1 of PloidyPlot.c:1489; analysis_in_core_1 :454-568, analysis_thread_1
  * :168-301, big_window :712-842): for every entry x in [lo,hi) find every one-substitution
  * neighbour y > x in the table; for each such pair with cnt sum <= SMAX add 1 to deg[x] and
@@ -95,13 +111,26 @@ int     hm_pick_filter_bits(int64_t n);
 int hm_k_pass1_degree(const uint64_t *d_keys, const uint16_t *d_cnt, int64_t n,
                       const void *d_bucket, int bits, int idx64,
                       const uint32_t *d_filter, int filter_bits, int kmer,
-                      int64_t lo, int64_t hi, uint8_t *d_deg, void *d_up, void *stream);
+                      int64_t lo, int64_t hi, uint8_t *d_deg, void *d_up,
+                      const hm_shards *shards, void *stream);
 
 /* Pass 2 (PASS1=0; analysis_in_core_2 :570-700, analysis_thread_2 :303-452): for x in [lo,hi)
  * with deg[x]<=1 whose recorded upper partner y has deg[y]<=1: plot[cx+cy][min(cx,cy)] += 1.
  * d_plot: uint64[HM_PLOT_CELLS], accumulated into (caller zeroes it).                        */
 int hm_k_pass2_plot(const uint16_t *d_cnt, const uint8_t *d_deg, const void *d_up, int idx64,
-                    int64_t lo, int64_t hi, unsigned long long *d_plot, void *stream);
+                    int64_t lo, int64_t hi, unsigned long long *d_plot,
+                    const hm_shards *shards, void *stream);
+
+/* Device memory that can be mapped by the other ranks of a one-process-per-GPU job (CUDA IPC):
+ * hm_dev_alloc gives a zeroed base allocation on the current device, hm_ipc_export its 64-byte
+ * handle (send it to the peers with any host transport), hm_ipc_open maps a peer's allocation.
+ * hm_p2p_native_atomics: 1 iff devices a and b can do remote atomics on each other (NVLink).    */
+int hm_dev_alloc(int64_t bytes, void **dptr);
+int hm_dev_free(void *dptr);
+int hm_ipc_export(void *dptr, unsigned char handle[64]);
+int hm_ipc_open(const unsigned char handle[64], void **dptr);
+int hm_ipc_close(void *dptr);
+int hm_p2p_native_atomics(int dev_a, int dev_b);
 
 /* examine_table (PloidyPlot.c:1167-1197): smallest count v>=1 (read as int16) in [frst,last);
  * *d_min (device int) must be preset to 0x8000.                                               */

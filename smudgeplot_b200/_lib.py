@@ -20,6 +20,7 @@ ABI_SYMBOLS = [
     "hm_k_unpack_records", "hm_k_build_bucket_index", "hm_k_pass1_degree", "hm_k_pass2_plot",
     "hm_k_min_count", "hm_k_find_keys", "hm_pick_bucket_bits",
     "hm_k_build_filter", "hm_filter_words", "hm_pick_filter_bits",
+    "hm_dev_alloc", "hm_dev_free", "hm_ipc_export", "hm_ipc_open", "hm_ipc_close", "hm_p2p_native_atomics",
     "hm_scan_create", "hm_scan_destroy", "hm_scan_examine", "hm_scan_run", "hm_hetmers_host",
     "hm_scan_download", "hm_table_open", "hm_table_close", "hm_table_view", "hm_write_smu",
 ]
@@ -29,6 +30,15 @@ class HostTable(C.Structure):
     _fields_ = [("kmer", C.c_int32), ("ibyte", C.c_int32), ("nparts", C.c_int32), ("minval", C.c_int32),
                 ("nels", C.c_int64), ("index", C.POINTER(C.c_int64)), ("part_nels", C.POINTER(C.c_int64)),
                 ("part_rec", C.POINTER(C.c_void_p))]
+
+
+MAX_SHARDS = 16
+
+
+class Shards(C.Structure):
+    """hm_shards: shard offsets + every owner's full-length incidence array as seen from this GPU"""
+    _fields_ = [("n_shards", C.c_int32), ("self_", C.c_int32), ("off", C.c_int64 * (MAX_SHARDS + 1)),
+                ("deg", C.c_void_p * MAX_SHARDS)]
 
 
 class ScanStats(C.Structure):
@@ -64,12 +74,18 @@ def lib():
     L.hm_device_info.argtypes = [i32, C.c_char_p, i32, C.POINTER(i32), C.POINTER(i64)]
     L.hm_k_unpack_records.argtypes = [vp, i64, i64, vp, i32, i32, vp, vp, vp]
     L.hm_k_build_bucket_index.argtypes = [vp, i64, i32, vp, i32, vp]
-    L.hm_k_pass1_degree.argtypes = [vp, vp, i64, vp, i32, i32, vp, i32, i32, i64, i64, vp, vp, vp]
+    L.hm_k_pass1_degree.argtypes = [vp, vp, i64, vp, i32, i32, vp, i32, i32, i64, i64, vp, vp, C.POINTER(Shards), vp]
+    L.hm_dev_alloc.argtypes = [i64, C.POINTER(vp)]
+    L.hm_dev_free.argtypes = [vp]
+    L.hm_ipc_export.argtypes = [vp, C.c_char_p]
+    L.hm_ipc_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.hm_ipc_close.argtypes = [vp]
+    L.hm_p2p_native_atomics.argtypes = [i32, i32]
     L.hm_k_build_filter.argtypes = [vp, i64, i32, vp, vp]
     L.hm_filter_words.argtypes = [i32]
     L.hm_filter_words.restype = i64
     L.hm_pick_filter_bits.argtypes = [i64]
-    L.hm_k_pass2_plot.argtypes = [vp, vp, vp, i32, i64, i64, vp, vp]
+    L.hm_k_pass2_plot.argtypes = [vp, vp, vp, i32, i64, i64, vp, C.POINTER(Shards), vp]
     L.hm_k_min_count.argtypes = [vp, i64, i64, vp, vp]
     L.hm_k_find_keys.argtypes = [vp, i64, vp, i32, i32, vp, i64, vp, vp]
     L.hm_pick_bucket_bits.argtypes = [i64]

@@ -341,14 +341,50 @@ extern "C" int hm_k_build_filter(const uint64_t *d_keys, int64_t n, int filter_b
 #define P1_QCAP    64           /* per-warp candidate queue: < 32 left + <= 32 pushed */
 #define P1_RUNCAP  12           /* forward scan bound for the high positions          */
 
+/* Where the incidence bytes live.  One GPU / dense mode: everything in `self`.  Sharded mode
+ * (DESIGN.md §6): every GPU has a full-length array but only the slice of the entries it OWNS is
+ * meaningful; bytes of foreign entries are reached through the owner's array, mapped here over
+ * NVLink (peer access in one process, CUDA IPC between processes).  Pass 1's increments to a
+ * foreign partner are remote atomics, pass 2's look-ups of a foreign partner are remote loads:
+ * the exchange step is fused into the two kernels, no collective moves the array.             */
+struct DegView
+  { uint32_t *self;
+    int64_t   lo, hi;                          /* entries owned by this GPU                      */
+    int       n;                               /* shards (0 = everything is local)               */
+    int64_t   off[HM_MAX_SHARDS+1];
+    uint32_t *peer[HM_MAX_SHARDS];
+  };
+
+static DegView make_deg_view(uint8_t *d_deg, int64_t lo, int64_t hi, const hm_shards *sh)
+{ DegView v;
+  memset(&v,0,sizeof(v));
+  v.self = (uint32_t *) d_deg;
+  if (sh == NULL || sh->n_shards <= 1)
+    { v.lo = INT64_MIN; v.hi = INT64_MAX; v.n = 0; }
+  else
+    { v.lo = lo; v.hi = hi; v.n = sh->n_shards;
+      for (int r = 0; r <= sh->n_shards; r++) v.off[r] = sh->off[r];
+      for (int r = 0; r < sh->n_shards; r++)  v.peer[r] = (uint32_t *) sh->deg[r];
+    }
+  return v;
+}
+
+__device__ __forceinline__ uint32_t *deg_words(const DegView &v, int64_t j)
+{ if (j >= v.lo && j < v.hi)
+    return v.self;
+  int r = 0;
+  while (r+1 < v.n && j >= v.off[r+1])
+    r += 1;
+  return v.peer[r];
+}
+
 /* book one qualifying pair (oi < j): both incidence bytes, and the upper partner of oi */
 template <typename IdxT>
 __device__ __forceinline__ void book_pair(const uint16_t *__restrict__ cnt, int64_t oi, int64_t j,
-                                          int64_t lo, uint32_t *__restrict__ deg32,
-                                          IdxT *__restrict__ up)
+                                          int64_t lo, const DegView &dv, IdxT *__restrict__ up)
 { if ((int) __ldg(cnt+oi) + (int) __ldg(cnt+j) <= HM_SMAX)         /* PloidyPlot.c:259 */
-    { atomicAdd(deg32 + (oi>>2), 1u << (8*(oi&3)));
-      atomicAdd(deg32 + (j>>2),  1u << (8*(j&3)));
+    { atomicAdd(dv.self + (oi>>2), 1u << (8*(oi&3)));
+      atomicAdd(deg_words(dv,j) + (j>>2), 1u << (8*(j&3)));
       up[oi-lo] = (IdxT) j;
     }
 }
@@ -372,7 +408,7 @@ __global__ void __launch_bounds__(P1_WARPS*32,P1_MINBLOCKS)
 pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restrict__ cnt,
                     int64_t n, const IdxT *__restrict__ bucket, int bshift,
                     const uint32_t *__restrict__ filter, int kmer,
-                    int64_t lo, int64_t hi, uint32_t *__restrict__ deg32, IdxT *__restrict__ up)
+                    int64_t lo, int64_t hi, const DegView dv, IdxT *__restrict__ up)
 { __shared__ uint64_t s_qy[P1_WARPS][P1_QCAP];
   __shared__ IdxT     s_qi[P1_WARPS][P1_QCAP];
 
@@ -467,7 +503,7 @@ pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restric
                     break;
                   uint64_t t = (dd | (dd>>1)) & 0x5555555555555555ull;
                   if ((t & (t-1)) == 0)                    /* exactly one base differs */
-                    book_pair<IdxT>(cnt,i,j,lo,deg32,up);
+                    book_pair<IdxT>(cnt,i,j,lo,dv,up);
                   j += 1;
                   if (j >= n)
                     break;
@@ -517,7 +553,7 @@ pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restric
               __syncwarp();
               int64_t j = bucket_find<IdxT>(keys,bucket,bshift,yy);
               if (j >= 0)
-                book_pair<IdxT>(cnt,oi,j,lo,deg32,up);
+                book_pair<IdxT>(cnt,oi,j,lo,dv,up);
             }
         }
     }
@@ -527,14 +563,14 @@ pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restric
       int64_t  oi = (int64_t) qi[lane];
       int64_t  j  = bucket_find<IdxT>(keys,bucket,bshift,yy);
       if (j >= 0)
-        book_pair<IdxT>(cnt,oi,j,lo,deg32,up);
+        book_pair<IdxT>(cnt,oi,j,lo,dv,up);
     }
 }
 
 template <typename IdxT, int F>
 static cudaError_t launch_pass1(const uint64_t *keys, const uint16_t *cnt, int64_t n,
                                 const void *bucket, int bits, const uint32_t *filter, int kmer,
-                                int64_t lo, int64_t hi, uint8_t *deg, void *up, cudaStream_t st)
+                                int64_t lo, int64_t hi, const DegView &dv, void *up, cudaStream_t st)
 { int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms,cudaDevAttrMultiProcessorCount,dev);
@@ -543,17 +579,17 @@ static cudaError_t launch_pass1(const uint64_t *keys, const uint16_t *cnt, int64
   int64_t cap     = (int64_t) sms*8*4;            /* 4 waves of 8 resident CTAs per SM */
   int     grid    = (int) (want < cap ? want : cap);
   pass1_filter_kernel<IdxT,F><<<grid,P1_WARPS*32,0,st>>>
-      (keys,cnt,n,(const IdxT *) bucket,64-bits,filter,kmer,lo,hi,(uint32_t *) deg,(IdxT *) up);
+      (keys,cnt,n,(const IdxT *) bucket,64-bits,filter,kmer,lo,hi,dv,(IdxT *) up);
   return cudaGetLastError();
 }
 
 template <typename IdxT>
 static cudaError_t dispatch_pass1(int fb, const uint64_t *keys, const uint16_t *cnt, int64_t n,
                                   const void *bucket, int bits, const uint32_t *filter, int kmer,
-                                  int64_t lo, int64_t hi, uint8_t *deg, void *up, cudaStream_t st)
+                                  int64_t lo, int64_t hi, const DegView &dv, void *up, cudaStream_t st)
 { switch (fb)
   {
-#define CASE(P) case P: return launch_pass1<IdxT,P>(keys,cnt,n,bucket,bits,filter,kmer,lo,hi,deg,up,st);
+#define CASE(P) case P: return launch_pass1<IdxT,P>(keys,cnt,n,bucket,bits,filter,kmer,lo,hi,dv,up,st);
     CASE(22) CASE(23) CASE(24) CASE(25) CASE(26) CASE(27) CASE(28) CASE(29)
     CASE(30) CASE(31) CASE(32) CASE(33) CASE(34) CASE(35) CASE(36) CASE(37)
 #undef CASE
@@ -564,7 +600,8 @@ static cudaError_t dispatch_pass1(int fb, const uint64_t *keys, const uint16_t *
 extern "C" int hm_k_pass1_degree(const uint64_t *d_keys, const uint16_t *d_cnt, int64_t n,
                                  const void *d_bucket, int bits, int idx64,
                                  const uint32_t *d_filter, int filter_bits, int kmer,
-                                 int64_t lo, int64_t hi, uint8_t *d_deg, void *d_up, void *stream)
+                                 int64_t lo, int64_t hi, uint8_t *d_deg, void *d_up,
+                                 const hm_shards *shards, void *stream)
 { if (kmer < 1 || kmer > HM_MAX_KMER)
     return hm_set_error(HM_EUNSUPPORTED,"k-mer length %d not supported (1..%d)",kmer,HM_MAX_KMER);
   if (lo < 0 || hi > n || lo > hi || bits < 1 || bits > 30)
@@ -574,11 +611,16 @@ extern "C" int hm_k_pass1_degree(const uint64_t *d_keys, const uint16_t *d_cnt, 
     return hm_set_error(HM_EINVAL,"pass1: filter bits %d out of range",filter_bits);
   if (hi == lo)
     return HM_OK;
+  if (shards != NULL && shards->n_shards > 1 &&
+      (shards->n_shards > HM_MAX_SHARDS || shards->self < 0 || shards->self >= shards->n_shards ||
+       shards->off[shards->self] != lo || shards->off[shards->self+1] != hi))
+    return hm_set_error(HM_EINVAL,"pass1: [lo,hi) is not shard %d of the shard table",shards->self);
   cudaStream_t st = (cudaStream_t) stream;
+  DegView dv = make_deg_view(d_deg,lo,hi,shards);
   HM_CUDA(cudaMemsetAsync(d_up,0xFF,(idx64 ? 8 : 4)*(size_t) (hi-lo),st));   /* all-ones = none */
   cudaError_t e = idx64
-      ? dispatch_pass1<uint64_t>(filter_bits,d_keys,d_cnt,n,d_bucket,bits,d_filter,kmer,lo,hi,d_deg,d_up,st)
-      : dispatch_pass1<uint32_t>(filter_bits,d_keys,d_cnt,n,d_bucket,bits,d_filter,kmer,lo,hi,d_deg,d_up,st);
+      ? dispatch_pass1<uint64_t>(filter_bits,d_keys,d_cnt,n,d_bucket,bits,d_filter,kmer,lo,hi,dv,d_up,st)
+      : dispatch_pass1<uint32_t>(filter_bits,d_keys,d_cnt,n,d_bucket,bits,d_filter,kmer,lo,hi,dv,d_up,st);
   if (e != cudaSuccess)
     return hm_cuda_fail(e,"pass1_filter_kernel");
   return HM_OK;
@@ -596,7 +638,7 @@ extern "C" int hm_k_pass1_degree(const uint64_t *d_keys, const uint16_t *d_cnt, 
  * plot in shared memory (uint32) and flush once; the rest goes to 64-bit global atomics.      */
 template <typename IdxT>
 __global__ void __launch_bounds__(P2_THREADS,P2_CTAS_PER_SM)
-pass2_plot_kernel(const uint16_t *__restrict__ cnt, const uint8_t *__restrict__ deg,
+pass2_plot_kernel(const uint16_t *__restrict__ cnt, const DegView dv,
                   const IdxT *__restrict__ up, int64_t lo, int64_t hi,
                   unsigned long long *__restrict__ plot)
 { extern __shared__ uint32_t tile[];
@@ -605,10 +647,13 @@ pass2_plot_kernel(const uint16_t *__restrict__ cnt, const uint8_t *__restrict__ 
   __syncthreads();
   int64_t stride = (int64_t) gridDim.x * blockDim.x;
   for (int64_t i = lo + (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride)
-    { if (deg[i] > 1)
+    { if (((const uint8_t *) dv.self)[i] > 1)
         continue;
       IdxT j = up[i-lo];
-      if (j == IdxNone<IdxT>::value || __ldg(deg+j) > 1)
+      if (j == IdxNone<IdxT>::value)
+        continue;
+      const uint8_t *dj = (const uint8_t *) deg_words(dv,(int64_t) j);
+      if ((dj == (const uint8_t *) dv.self ? __ldg(dj+j) : __ldcv(dj+j)) > 1)   /* foreign: peer load */
         continue;
       int ci = cnt[i], cj = __ldg(cnt+j);
       int s  = ci+cj;
@@ -628,7 +673,7 @@ pass2_plot_kernel(const uint16_t *__restrict__ cnt, const uint8_t *__restrict__ 
 
 extern "C" int hm_k_pass2_plot(const uint16_t *d_cnt, const uint8_t *d_deg, const void *d_up,
                                int idx64, int64_t lo, int64_t hi, unsigned long long *d_plot,
-                               void *stream)
+                               const hm_shards *shards, void *stream)
 { static int configured[64] = {0};
   if (lo > hi)
     return hm_set_error(HM_EINVAL,"pass2: bad range");
@@ -649,12 +694,13 @@ extern "C" int hm_k_pass2_plot(const uint16_t *d_cnt, const uint8_t *d_deg, cons
     }
   int64_t want = (hi-lo+P2_THREADS-1)/P2_THREADS;
   int     grid = (int) (want < sms*P2_CTAS_PER_SM ? want : sms*P2_CTAS_PER_SM);
+  DegView dv   = make_deg_view((uint8_t *) d_deg,lo,hi,shards);
   if (idx64)
     pass2_plot_kernel<uint64_t><<<grid,P2_THREADS,smem,(cudaStream_t) stream>>>
-        (d_cnt,d_deg,(const uint64_t *) d_up,lo,hi,d_plot);
+        (d_cnt,dv,(const uint64_t *) d_up,lo,hi,d_plot);
   else
     pass2_plot_kernel<uint32_t><<<grid,P2_THREADS,smem,(cudaStream_t) stream>>>
-        (d_cnt,d_deg,(const uint32_t *) d_up,lo,hi,d_plot);
+        (d_cnt,dv,(const uint32_t *) d_up,lo,hi,d_plot);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return hm_cuda_fail(e,"pass2_plot_kernel");

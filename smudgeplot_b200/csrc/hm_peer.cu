@@ -16,6 +16,7 @@
  *******************************************************************************************/
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "hetmers_b200.h"
 #include "hm_internal.h"
@@ -43,6 +44,56 @@ int hm_peer_enable(const int *dev, int n)
         }
     }
   return HM_OK;
+}
+
+/* ---- CUDA IPC plumbing for the one-process-per-GPU job (layer A callers) ---- */
+
+extern "C" int hm_dev_alloc(int64_t bytes, void **dptr)
+{ if (bytes <= 0 || dptr == NULL)
+    return hm_set_error(HM_EINVAL,"hm_dev_alloc: bad arguments");
+  HM_CUDA(cudaMalloc(dptr,(size_t) bytes));
+  HM_CUDA(cudaMemset(*dptr,0,(size_t) bytes));
+  return HM_OK;
+}
+
+extern "C" int hm_dev_free(void *dptr)
+{ if (dptr != NULL)
+    HM_CUDA(cudaFree(dptr));
+  return HM_OK;
+}
+
+extern "C" int hm_ipc_export(void *dptr, unsigned char handle[64])
+{ cudaIpcMemHandle_t h;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64,"IPC handle size");
+  HM_CUDA(cudaIpcGetMemHandle(&h,dptr));
+  memcpy(handle,&h,64);
+  return HM_OK;
+}
+
+extern "C" int hm_ipc_open(const unsigned char handle[64], void **dptr)
+{ cudaIpcMemHandle_t h;
+  memcpy(&h,handle,64);
+  HM_CUDA(cudaIpcOpenMemHandle(dptr,h,cudaIpcMemLazyEnablePeerAccess));
+  return HM_OK;
+}
+
+extern "C" int hm_ipc_close(void *dptr)
+{ if (dptr != NULL)
+    HM_CUDA(cudaIpcCloseMemHandle(dptr));
+  return HM_OK;
+}
+
+extern "C" int hm_p2p_native_atomics(int dev_a, int dev_b)
+{ int ab = 0, ba = 0, can1 = 0, can2 = 0;
+  if (dev_a == dev_b)
+    return 1;
+  if (cudaDeviceCanAccessPeer(&can1,dev_a,dev_b) != cudaSuccess ||
+      cudaDeviceCanAccessPeer(&can2,dev_b,dev_a) != cudaSuccess || !can1 || !can2)
+    { cudaGetLastError(); return 0; }
+  if (cudaDeviceGetP2PAttribute(&ab,cudaDevP2PAttrNativeAtomicSupported,dev_a,dev_b) != cudaSuccess ||
+      cudaDeviceGetP2PAttribute(&ba,cudaDevP2PAttrNativeAtomicSupported,dev_b,dev_a) != cudaSuccess)
+    { cudaGetLastError(); return 0; }
+  return (ab && ba);
 }
 
 __global__ void __launch_bounds__(256)

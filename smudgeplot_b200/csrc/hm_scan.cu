@@ -9,7 +9,9 @@
  * Every device holds a full replica of the table (180 GB HBM3e holds 16e9 k=31 entries); work is
  * sharded by contiguous index range [lo_g, hi_g).  With one GPU there is no exchange at all.
  * With several GPUs in this single process the loader gathers the shards over NVLink peer
- * copies and the degree bytes are summed by a peer-memory kernel (hm_peer.cu); the
+ * copies and foreign degree bytes are reached through the owner's array (remote atomics / loads
+ * fused into the two kernels; summed by a peer-memory kernel of hm_peer.cu if there are no
+ * native NVLink atomics); the
  * one-process-per-GPU variant (torch.distributed / NCCL) lives in smudgeplot_b200/dist.py and
  * uses layer A directly.
  *******************************************************************************************/
@@ -302,6 +304,26 @@ extern "C" int hm_scan_run(hm_scan *s, int64_t *plot, hm_scan_stats *stats)
   cudaEvent_t ev[HM_MAX_GPUS][4];
   float       ms1 = 0, ms2 = 0, msall = 0;
 
+  /* several GPUs: foreign incidence bytes are reached through the owner's array (remote atomics
+   * in pass 1, remote loads in pass 2) when every pair of GPUs has native NVLink atomics; otherwise
+   * the partial arrays are summed by the peer-memory kernel of hm_peer.cu                        */
+  int       peer_mode = (G > 1);
+  hm_shards sh[HM_MAX_GPUS];
+  for (int a = 0; a < G && peer_mode; a++)
+    for (int b = a+1; b < G && peer_mode; b++)
+      if (!hm_p2p_native_atomics(s->d[a].dev,s->d[b].dev))
+        peer_mode = 0;
+  if (getenv("HETMERS_DENSE_EXCHANGE") != NULL)
+    peer_mode = 0;
+  if (peer_mode)
+    for (int g = 0; g < G; g++)
+      { memset(&sh[g],0,sizeof(hm_shards));
+        sh[g].n_shards = G; sh[g].self = g;
+        for (int r = 0; r < G; r++)
+          { sh[g].off[r] = s->d[r].lo; sh[g].deg[r] = s->d[r].deg; }
+        sh[g].off[G] = n;
+      }
+
   for (int g = 0; g < G; g++)
     { DevTable *D = s->d+g;
       HM_CUDA(cudaSetDevice(D->dev));
@@ -310,13 +332,20 @@ extern "C" int hm_scan_run(hm_scan *s, int64_t *plot, hm_scan_stats *stats)
       HM_CUDA(cudaEventRecord(ev[g][0],D->st));
       HM_CUDA(cudaMemsetAsync(D->deg,0,(size_t) ((n+4)&~3ll),D->st));
       HM_CUDA(cudaMemsetAsync(D->plot,0,sizeof(unsigned long long)*HM_PLOT_CELLS,D->st));
+    }
+  if (peer_mode)                                /* nobody adds to a peer before it has been zeroed */
+    for (int g = 0; g < G; g++)
+      { HM_CUDA(cudaSetDevice(s->d[g].dev)); HM_CUDA(cudaStreamSynchronize(s->d[g].st)); }
+  for (int g = 0; g < G; g++)
+    { DevTable *D = s->d+g;
+      HM_CUDA(cudaSetDevice(D->dev));
       rc = hm_k_pass1_degree(D->keys,D->cnt,n,D->bucket,s->bits,s->idx64,D->filter,s->fpos,s->kmer,
-                             D->lo,D->hi,D->deg,D->up,D->st);
+                             D->lo,D->hi,D->deg,D->up,peer_mode ? &sh[g] : NULL,D->st);
       if (rc != HM_OK) return rc;
       s->launches += (D->hi > D->lo);
       HM_CUDA(cudaEventRecord(ev[g][1],D->st));
     }
-  if (G > 1)
+  if (G > 1 && !peer_mode)
     { uint8_t *deg[HM_MAX_GPUS]; int64_t lo[HM_MAX_GPUS], hi[HM_MAX_GPUS];
       int dev[HM_MAX_GPUS]; cudaStream_t st[HM_MAX_GPUS];
       for (int g = 0; g < G; g++)
@@ -327,11 +356,15 @@ extern "C" int hm_scan_run(hm_scan *s, int64_t *plot, hm_scan_stats *stats)
       if (rc != HM_OK) return rc;
       s->launches += G;
     }
+  if (peer_mode)                                /* every pass 1 (and its remote atomics) has landed */
+    for (int g = 0; g < G; g++)
+      { HM_CUDA(cudaSetDevice(s->d[g].dev)); HM_CUDA(cudaStreamSynchronize(s->d[g].st)); }
   for (int g = 0; g < G; g++)
     { DevTable *D = s->d+g;
       HM_CUDA(cudaSetDevice(D->dev));
       HM_CUDA(cudaEventRecord(ev[g][2],D->st));
-      rc = hm_k_pass2_plot(D->cnt,D->deg,D->up,s->idx64,D->lo,D->hi,D->plot,D->st);
+      rc = hm_k_pass2_plot(D->cnt,D->deg,D->up,s->idx64,D->lo,D->hi,D->plot,
+                           peer_mode ? &sh[g] : NULL,D->st);
       if (rc != HM_OK) return rc;
       s->launches += (D->hi > D->lo);
       HM_CUDA(cudaEventRecord(ev[g][3],D->st));
@@ -396,7 +429,13 @@ extern "C" int hm_scan_download(hm_scan *s, uint64_t *keys, uint16_t *cnt, uint8
     HM_CUDA(cudaMemcpy(keys,D->keys,sizeof(uint64_t)*(size_t) s->n,cudaMemcpyDeviceToHost));
   if (cnt != NULL)
     HM_CUDA(cudaMemcpy(cnt,D->cnt,sizeof(uint16_t)*(size_t) s->n,cudaMemcpyDeviceToHost));
-  if (deg != NULL)
-    HM_CUDA(cudaMemcpy(deg,D->deg,(size_t) s->n,cudaMemcpyDeviceToHost));
+  if (deg != NULL)                      /* every owner's slice (identical copies in dense mode) */
+    for (int g = 0; g < s->ngpu; g++)
+      { DevTable *O = s->d+g;
+        HM_CUDA(cudaSetDevice(O->dev));
+        HM_CUDA(cudaStreamSynchronize(O->st));
+        if (O->hi > O->lo)
+          HM_CUDA(cudaMemcpy(deg+O->lo,O->deg+O->lo,(size_t) (O->hi-O->lo),cudaMemcpyDeviceToHost));
+      }
   return HM_OK;
 }

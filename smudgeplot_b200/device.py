@@ -45,6 +45,8 @@ class DeviceTable:
         self.up = None
         self.lo = self.hi = 0
         self.launches = 0
+        self.shards = None          # _lib.Shards when the incidence array is sharded over GPUs
+        self.deg_ptr = None         # raw device pointer overriding self.deg (IPC-shared allocation)
 
     # ---- construction -------------------------------------------------------------------
     @classmethod
@@ -93,20 +95,27 @@ class DeviceTable:
         self.plot = torch.zeros(_lib.PLOT_CELLS, dtype=torch.int64, device=self.device)
         return self
 
+    def _deg(self):
+        return self.deg_ptr if self.deg_ptr is not None else _ptr(self.deg)
+
+    def _shards(self):
+        import ctypes as C
+        return C.byref(self.shards) if self.shards is not None else None
+
     def pass1(self):
         """neighbour search + degree (hm_k_pass1_degree) over [lo,hi); deg must be zero."""
         with torch.cuda.device(self.device):
             _lib.check(self.L.hm_k_pass1_degree(_ptr(self.keys), _ptr(self.cnt), self.n, _ptr(self.bucket),
                                                 self.bits, self.idx64, _ptr(self.filter), self.fbits, self.kmer,
                                                 self.lo, self.hi,
-                                                _ptr(self.deg), _ptr(self.up), _stream()))
+                                                self._deg(), _ptr(self.up), self._shards(), _stream()))
         self.launches += 1
 
     def pass2(self):
         """isolated pairs -> plot (hm_k_pass2_plot) over [lo,hi); accumulates into self.plot."""
         with torch.cuda.device(self.device):
-            _lib.check(self.L.hm_k_pass2_plot(_ptr(self.cnt), _ptr(self.deg), _ptr(self.up), self.idx64,
-                                              self.lo, self.hi, _ptr(self.plot), _stream()))
+            _lib.check(self.L.hm_k_pass2_plot(_ptr(self.cnt), self._deg(), _ptr(self.up), self.idx64,
+                                              self.lo, self.hi, _ptr(self.plot), self._shards(), _stream()))
         self.launches += 1
 
     def scan(self):

@@ -65,6 +65,15 @@ def gather_table(local_keys: torch.Tensor, local_cnt: torch.Tensor, group=None, 
     return keys, cnt, lo, hi
 
 
+def _cuda_view(ptr: int, nbytes: int, device) -> torch.Tensor:
+    """uint8 tensor over a raw device allocation (no ownership) via __cuda_array_interface__"""
+    class _Raw:
+        pass
+    r = _Raw()
+    r.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(r, device=device)
+
+
 def allreduce_deg(deg: torch.Tensor, group=None):
     """sum of the partial incidence arrays (uint8; no wrap: <= 3k <= 96 neighbours for k <= 32)"""
     dist.all_reduce(deg, op=dist.ReduceOp.SUM, group=group)
@@ -74,6 +83,77 @@ def allreduce_deg(deg: torch.Tensor, group=None):
 def allreduce_plot(plot: torch.Tensor, group=None):
     dist.all_reduce(plot, op=dist.ReduceOp.SUM, group=group)
     return plot
+
+
+class PeerDeg:
+    """The sharded incidence array of DESIGN.md §6 for a one-process-per-GPU job: every rank
+    cudaMallocs its own full-length array through the C ABI (hm_dev_alloc), exports a CUDA IPC
+    handle, and maps everybody else's (hm_ipc_open).  With it the exchange between the passes is
+    fused into the kernels (remote atomics / remote loads over NVLink) and no collective moves the
+    array.  `PeerDeg.create` returns None when IPC or native NVLink atomics are unavailable, and
+    the caller falls back to the dense all-reduce."""
+
+    def __init__(self, own, peers, nbytes, rank):
+        self.own, self.peers, self.nbytes, self.rank = own, peers, nbytes, rank
+
+    @classmethod
+    def create(cls, n, device, group=None):
+        import ctypes as C
+        import os
+        from . import _lib
+        if os.environ.get("HETMERS_DENSE_EXCHANGE"):
+            return None
+        L = _lib.lib()
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        nbytes = (n + 256) & ~255               # one buffer; the allocation holds TWO (see scan_on)
+        ok = 1
+        own = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        with torch.cuda.device(device):
+            if L.hm_dev_alloc(2 * nbytes, C.byref(own)) != 0 or L.hm_ipc_export(own, handle) != 0:
+                ok = 0
+        info = [None] * world
+        dist.all_gather_object(info, (ok, handle.raw, torch.cuda.current_device() if device.index is None else device.index),
+                               group=group)
+        peers = [None] * world
+        if all(i[0] for i in info):
+            for r, (_, h, dev_r) in enumerate(info):
+                if r == rank:
+                    peers[r] = own.value
+                    continue
+                if not L.hm_p2p_native_atomics(device.index or 0, dev_r):
+                    ok = 0
+                    break
+                ptr = C.c_void_p()
+                with torch.cuda.device(device):
+                    if L.hm_ipc_open(h, C.byref(ptr)) != 0:
+                        ok = 0
+                        break
+                peers[r] = ptr.value
+        else:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            with torch.cuda.device(device):
+                for r, pp in enumerate(peers):
+                    if pp is not None and r != rank:
+                        L.hm_ipc_close(C.c_void_p(pp))
+                if own.value:
+                    L.hm_dev_free(own)
+            return None
+        return cls(own.value, peers, nbytes, rank)
+
+    def shards(self, offsets, parity):
+        """hm_shards over buffer `parity` (0/1) of every rank's allocation"""
+        from . import _lib
+        sh = _lib.Shards()
+        sh.n_shards, sh.self_ = len(self.peers), self.rank
+        for r, o in enumerate(offsets):
+            sh.off[r] = o
+        for r, pp in enumerate(self.peers):
+            sh.deg[r] = pp + parity * self.nbytes
+        return sh
 
 
 class ShardedScan:
@@ -89,7 +169,17 @@ class ShardedScan:
         self.kmer, self.lo, self.hi = kmer, lo, hi
         self.n_total = keys_full.numel()
         self.bits = self.table.bits
-        self._shard_src = None
+        # shard table (index offsets of every rank) and, if possible, the peer-mapped incidence arrays
+        sizes, offs, total = shard_offsets(hi - lo, group, keys_full.device)
+        self.offsets = offs + [total]
+        self.peer = PeerDeg.create(self.n_total, keys_full.device, group) if self.world > 1 else None
+        self.exchange = "peer-memory (remote atomics/loads over NVLink, CUDA IPC)" if self.peer else \
+                        ("all-reduce(uint8[n]) via NCCL" if self.world > 1 else "none")
+        self._barrier_t = torch.zeros(1, dtype=torch.int32, device=keys_full.device)
+        self._step = 0
+        if self.peer is not None:       # tensors over the two halves of the IPC allocation (no ownership)
+            self._peer_views = [_cuda_view(self.peer.own + h * self.peer.nbytes, self.peer.nbytes, keys_full.device)
+                                for h in (0, 1)]
 
     @classmethod
     def from_synthetic(cls, k, G, ploidy, het, cov, L, seed, device, group=None):
@@ -106,17 +196,45 @@ class ShardedScan:
         return cls(k, kf, cf, lo, hi, group)
 
     def scan(self, events=None):
-        t = self.table
-        t.deg.zero_()
+        return self.scan_on(self.table, events)
+
+    def scan_on(self, t, events=None):
+        """one T_scan on table replica `t` (self.table for the resident scans, a freshly loaded
+        replica in the e2e leg).  Peer mode keeps the phases ordered with two collectives per scan:
+        a 4-byte all-reduce after pass 1 (every remote atomic has landed before any pass 2 reads),
+        and the plot all-reduce after pass 2.  The incidence array is double-buffered: scan s uses
+        buffer s&1 and clears the other one after the first barrier -- by then every rank has left
+        pass 2 of scan s-1 (it could not have passed that scan's plot all-reduce otherwise), and
+        nobody writes it before the plot all-reduce of scan s, which the clearing rank joins only
+        after its memset (stream order)."""
+        if self.peer is None:
+            t.deg.zero_()
+            t.plot.zero_()
+            if events is not None:
+                events[0].record()
+            t.pass1()
+            if events is not None:
+                events[1].record()
+            if self.world > 1:
+                allreduce_deg(t.deg, self.group)
+            t.pass2()
+            if self.world > 1:
+                allreduce_plot(t.plot, self.group)
+            return t.plot
+        par = self._step & 1
+        self._step += 1
+        t.deg_ptr = self.peer.own + par * self.peer.nbytes
+        t.shards = self.peer.shards(self.offsets, par)
         t.plot.zero_()
         if events is not None:
             events[0].record()
         t.pass1()
         if events is not None:
             events[1].record()
-        allreduce_deg(t.deg, self.group)
+        dist.all_reduce(self._barrier_t, group=self.group)            # all pass 1 kernels have landed
         t.pass2()
-        allreduce_plot(t.plot, self.group)
+        self._peer_views[par ^ 1].zero_()                             # the next scan's buffer ...
+        allreduce_plot(t.plot, self.group)                            # ... is clear before anybody can use it
         return t.plot
 
     # ---- end-to-end from pinned host buffers (bench.py e2e leg) -----------------------------
@@ -158,10 +276,7 @@ class ShardedScan:
             gather_table(k2[lo:hi], c2[lo:hi], self.group, out=(k2, c2))
             tt = DeviceTable(k, k2, c2, bits=self.bits).build_index()
             tt.alloc_work(lo, hi)
-            tt.pass1()
-            allreduce_deg(tt.deg, self.group)
-            tt.pass2()
-            allreduce_plot(tt.plot, self.group)
+            self.scan_on(tt)
             if self.rank == 0:
                 h_plot.copy_(tt.plot, non_blocking=True)
             torch.cuda.synchronize()
@@ -185,4 +300,4 @@ class ShardedScan:
                 "d2h_bytes_per_step": int(_lib.PLOT_CELLS * 8),
                 "api": "smudgeplot_b200.dist: pinned shard records -> H2D -> hm_k_unpack_records -> shard broadcast "
                        "(NCCL) -> hm_k_build_bucket_index -> pass1 -> all-reduce(deg) -> pass2 -> all-reduce(plot) -> D2H",
-                "plot_matches_resident_scan": same}
+                "plot_matches_resident_scan": same, "exchange": self.exchange}

@@ -246,3 +246,63 @@ def test_multi_gpu_single_process_matches_single_gpu(ngpu, tmp_path):
     out = str(tmp_path / "o")
     hetmers.run_hetmers(name, o=out, L=12, t=4, gpus=ngpu)
     assert open(out + ".smu").read() == hetmers.smu_text(one)
+
+
+def test_multi_gpu_dense_exchange_fallback(tmp_path, monkeypatch):
+    """same as above through the dense route (partial arrays summed by the peer-memory kernel),
+    which is what runs when the GPUs have no native NVLink atomics"""
+    if _lib.lib().hm_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    keys, cnt = synth.synth_table(27, 300000, 2, 0.02, 40, 6, 9, device="cuda")
+    kt = synth.write_table(str(tmp_path / "t"), 27, keys, cnt, ibyte=3, nparts=2)
+    one, _ = hetmers.scan_table(kt, gpus=1)
+    monkeypatch.setenv("HETMERS_DENSE_EXCHANGE", "1")
+    many, _ = hetmers.scan_table(kt, gpus=2)
+    assert np.array_equal(one, many)
+
+
+def _dist_worker(rank, world, port, q, dense):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if dense:
+        os.environ["HETMERS_DENSE_EXCHANGE"] = "1"
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from smudgeplot_b200 import dist as hd
+        job = hd.ShardedScan.from_synthetic(31, 500000, 3, 0.01, 60, 12, 4, torch.device("cuda", rank))
+        plots = [job.scan().clone().cpu().numpy() for _ in range(3)]       # repeated: double buffering
+        q.put((rank, job.exchange, plots, job.n_total))
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dense", [False, True])
+def test_one_process_per_gpu_nccl_matches_single_gpu(dense):
+    """torch.distributed/NCCL route (bench.py --gpus N): peer-mapped incidence arrays over CUDA IPC,
+    and the dense all-reduce fallback, against a single-GPU scan of the same seeded table"""
+    import torch
+    import torch.multiprocessing as mp
+    from smudgeplot_b200.device import DeviceTable
+    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 1000) + int(dense)
+    procs = [ctx.Process(target=_dist_worker, args=(r, world, port, q, dense)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    keys, cnt = synth.synth_table(31, 500000, 3, 0.01, 60, 12, 4, device="cuda")
+    want = DeviceTable(31, keys, cnt.to(torch.int16)).build_index().scan().cpu().numpy().reshape(-1)
+    for rank, exchange, plots, n_total in res:
+        assert n_total == keys.numel()
+        assert ("NCCL" in exchange) == dense, exchange
+        for p in plots:
+            assert np.array_equal(p.reshape(-1), want)
