@@ -34,7 +34,7 @@ $(OBJDIR)/fastk_table.o: smudgeplot_b200/host/fastk_table.c $(HDRS)
 
 $(LIB): $(CU_OBJ) $(C_OBJ)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) -shared $(ARCH) -o $@ $^ -cudart static
+	$(NVCC) -shared $(ARCH) -o $@ $^ -cudart static -lpthread
 
 $(BIN): smudgeplot_b200/host/hetmers_main.c $(LIB) $(HDRS)
 	@mkdir -p $(BINDIR)

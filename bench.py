@@ -273,6 +273,8 @@ def run_ours(args):
         one_scan()
     torch.cuda.synchronize()
     if multi:
+        job.profile_phases = True
+    if multi:
         dist.barrier()
     # ---- timed region: exactly K steps ------------------------------------------------------
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -290,6 +292,8 @@ def run_ours(args):
         ms_p1 = sum(a.elapsed_time(b) for a, b in p1) / args.steps
         # keep the sampler alive over the e2e region too (more samples under load)
         e2e = None
+        if multi:
+            job.profile_phases = False
         if not args.no_e2e:
             e2e = measure_e2e(args, torch, dist, dev, multi, world, rank,
                               job if multi else None, (keys, cnt) if not multi else None)
@@ -317,6 +321,10 @@ def run_ours(args):
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "algorithmic_bytes_per_kmer": ALGO_BYTES_PER_KMER, "ms_per_launch": ms_p1,
                          "traffic": measured_traffic(per_launch)}}
+    if multi and job.phase_ms():
+        allp = [None] * world
+        dist.all_gather_object(allp, {k: round(v, 3) for k, v in job.phase_ms().items()})
+        line["config"]["phases_ms_per_rank"] = allp
     if e2e is not None:
         line["e2e"] = e2e
     if rank == 0:

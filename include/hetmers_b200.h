@@ -177,6 +177,9 @@ typedef struct hm_scan hm_scan;   /* opaque: device-resident table + work buffer
  * work is sharded by contiguous index range).  Replaces Open_Kmer_Stream +
  * Clone_Kmer_Stream + the 4 GiB cache fill (libfastk.c:786-951; PloidyPlot.c:954-964).       */
 int  hm_scan_create(const hm_host_table *t, const int *dev, int n_gpus, hm_scan **out);
+/* host threads used to stage pageable (e.g. mmap'ed) part payloads into pinned memory during
+ * hm_scan_create; 0 = min(16, cores).  The executable passes its -T here.                      */
+void hm_set_io_threads(int n);
 void hm_scan_destroy(hm_scan *s);
 /* examine_table decisions (PloidyPlot.c:1167-1230) computed on the device */
 int  hm_scan_examine(hm_scan *s, int ethresh, int *trim, int *symm);

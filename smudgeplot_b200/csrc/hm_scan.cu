@@ -21,6 +21,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <pthread.h>
+#include <unistd.h>
 
 #include "hetmers_b200.h"
 #include "hm_internal.h"
@@ -83,23 +85,84 @@ extern "C" void hm_scan_destroy(hm_scan *s)
   free(s);
 }
 
+/* ---- host-side staging for pageable sources (mmap'ed part files) -------------------------
+ * cudaMemcpyAsync from pageable memory is staged by the driver on one thread (~3-6 GB/s).  The
+ * executable's table lives in the page cache, so the loader copies each chunk into a pinned
+ * buffer with a few host threads (this is what the reference's -T is for on the host side) while
+ * the previous chunk is in flight to the GPU.                                                   */
+static int g_io_threads = 0;
+
+extern "C" void hm_set_io_threads(int n) { g_io_threads = n; }
+
+typedef struct { uint8_t *dst; const uint8_t *src; size_t bytes; } CopyJob;
+
+static void *copy_worker(void *arg)
+{ CopyJob *j = (CopyJob *) arg;
+  memcpy(j->dst,j->src,j->bytes);
+  return NULL;
+}
+
+static void parallel_memcpy(uint8_t *dst, const uint8_t *src, size_t bytes)
+{ int nt = g_io_threads;
+  if (nt <= 0)
+    { long c = sysconf(_SC_NPROCESSORS_ONLN);
+      nt = c > 16 ? 16 : (c < 1 ? 1 : (int) c);
+    }
+  if (nt > 64) nt = 64;
+  if (bytes < ((size_t) 4<<20)) nt = 1;
+  pthread_t th[64];
+  CopyJob   job[64];
+  size_t    per = ((bytes/nt)+4095) & ~(size_t) 4095;
+  int       started = 0;
+  for (int k = 0; k < nt; k++)
+    { size_t off = per*k;
+      if (off >= bytes) break;
+      job[k].dst = dst+off; job[k].src = src+off;
+      job[k].bytes = bytes-off < per ? bytes-off : per;
+      if (k == nt-1 || off+per >= bytes)
+        { copy_worker(job+k); break; }                 /* the calling thread takes the last slice */
+      if (pthread_create(th+k,NULL,copy_worker,job+k) != 0)
+        { copy_worker(job+k); continue; }
+      started = k+1;
+    }
+  for (int k = 0; k < started; k++)
+    pthread_join(th[k],NULL);
+}
+
+static int is_pageable(const void *p)
+{ cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a,p) != cudaSuccess)
+    { cudaGetLastError(); return 1; }
+  return (a.type == cudaMemoryTypeUnregistered);
+}
+
 /* Load ordinals [first, first+count) of the table onto device D (keys/cnt already allocated for
- * the full table).  Walks the parts, copies payload chunks H2D on st_copy into one of two staging
- * buffers and unpacks them on st.                                                              */
+ * the full table).  Walks the parts, copies payload chunks H2D on st_copy into one of two device
+ * staging buffers and unpacks them on st (copy of chunk c+1 overlaps the unpack of chunk c);
+ * pageable sources additionally go through two pinned host buffers filled by host threads.      */
 static int load_range(hm_scan *s, DevTable *D, const hm_host_table *t, const int64_t *d_index,
                       int64_t first, int64_t count)
 { int      kbyte = (t->kmer+3)>>2;
   int      pbyte = kbyte - t->ibyte + 2;
   uint8_t *stage[2] = { NULL, NULL };
+  uint8_t *pin[2]   = { NULL, NULL };
   cudaEvent_t copied[2], unpacked[2];
   int64_t  chunk = LOAD_CHUNK;
   int      rc = HM_OK, b = 0, used[2] = {0,0};
+  int      staged = 0;
 
   if (count <= 0)
     return HM_OK;
+  for (int p = 0; p < t->nparts && !staged; p++)
+    if (t->part_nels[p] > 0 && is_pageable(t->part_rec[p]))
+      staged = 1;
+  if (staged)
+    chunk = LOAD_CHUNK/2;
   if (chunk > count) chunk = count;
   for (int i = 0; i < 2; i++)
     { HM_CUDA(cudaMalloc(&stage[i],(size_t) chunk*pbyte));
+      if (staged)
+        HM_CUDA(cudaHostAlloc(&pin[i],(size_t) chunk*pbyte,cudaHostAllocDefault));
       HM_CUDA(cudaEventCreateWithFlags(&copied[i],cudaEventDisableTiming));
       HM_CUDA(cudaEventCreateWithFlags(&unpacked[i],cudaEventDisableTiming));
     }
@@ -109,11 +172,17 @@ static int load_range(hm_scan *s, DevTable *D, const hm_host_table *t, const int
       int64_t from = first > pstart ? first : pstart;
       int64_t to   = first+count < pstart+pn ? first+count : pstart+pn;
       for (int64_t o = from; o < to && rc == HM_OK; o += chunk)
-        { int64_t m = to-o < chunk ? to-o : chunk;
+        { int64_t        m   = to-o < chunk ? to-o : chunk;
+          const uint8_t *src = t->part_rec[p] + (o-pstart)*pbyte;
+          if (staged)
+            { if (used[b])
+                cudaEventSynchronize(copied[b]);      /* pin[b] has left for the GPU */
+              parallel_memcpy(pin[b],src,(size_t) m*pbyte);
+              src = pin[b];
+            }
           if (used[b])
             cudaStreamWaitEvent(D->st_copy,unpacked[b],0);
-          cudaError_t e = cudaMemcpyAsync(stage[b],t->part_rec[p] + (o-pstart)*pbyte,
-                                          (size_t) m*pbyte,cudaMemcpyHostToDevice,D->st_copy);
+          cudaError_t e = cudaMemcpyAsync(stage[b],src,(size_t) m*pbyte,cudaMemcpyHostToDevice,D->st_copy);
           if (e != cudaSuccess) { rc = hm_cuda_fail(e,"cudaMemcpyAsync(H2D records)"); break; }
           cudaEventRecord(copied[b],D->st_copy);
           cudaStreamWaitEvent(D->st,copied[b],0);
@@ -128,7 +197,9 @@ static int load_range(hm_scan *s, DevTable *D, const hm_host_table *t, const int
   cudaStreamSynchronize(D->st_copy);
   cudaError_t e = cudaStreamSynchronize(D->st);
   for (int i = 0; i < 2; i++)
-    { cudaFree(stage[i]); cudaEventDestroy(copied[i]); cudaEventDestroy(unpacked[i]); }
+    { cudaFree(stage[i]); cudaEventDestroy(copied[i]); cudaEventDestroy(unpacked[i]);
+      if (pin[i] != NULL) cudaFreeHost(pin[i]);
+    }
   if (rc == HM_OK && e != cudaSuccess)
     rc = hm_cuda_fail(e,"unpack");
   return rc;

@@ -225,17 +225,41 @@ class ShardedScan:
         self._step += 1
         t.deg_ptr = self.peer.own + par * self.peer.nbytes
         t.shards = self.peer.shards(self.offsets, par)
+        ph = self._phase_events() if self.profile_phases else None
         t.plot.zero_()
         if events is not None:
             events[0].record()
+        if ph: ph[0].record()
         t.pass1()
         if events is not None:
             events[1].record()
+        if ph: ph[1].record()
         dist.all_reduce(self._barrier_t, group=self.group)            # all pass 1 kernels have landed
+        if ph: ph[2].record()
         t.pass2()
+        if ph: ph[3].record()
         self._peer_views[par ^ 1].zero_()                             # the next scan's buffer ...
+        if ph: ph[4].record()
         allreduce_plot(t.plot, self.group)                            # ... is clear before anybody can use it
+        if ph: ph[5].record()
         return t.plot
+
+    profile_phases = False
+
+    def _phase_events(self):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        self._phases = getattr(self, "_phases", [])
+        self._phases.append(ev)
+        return ev
+
+    def phase_ms(self):
+        """mean ms of (pass1, barrier, pass2, zero-next, plot all-reduce) over the profiled scans"""
+        torch.cuda.synchronize()
+        rows = [[a.elapsed_time(b) for a, b in zip(ev[:-1], ev[1:])] for ev in getattr(self, "_phases", [])]
+        if not rows:
+            return None
+        names = ["pass1", "barrier_after_pass1", "pass2", "zero_next_buffer", "plot_allreduce"]
+        return {n: sum(r[i] for r in rows) / len(rows) for i, n in enumerate(names)}
 
     # ---- end-to-end from pinned host buffers (bench.py e2e leg) -----------------------------
     def measure_e2e(self, steps, warmup):

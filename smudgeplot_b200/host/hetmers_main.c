@@ -17,7 +17,15 @@
 #include <string.h>
 #include <strings.h>
 
+#include <time.h>
+
 #include "hetmers_b200.h"
+
+static double wall_ms(void)
+{ struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC,&ts);
+  return ts.tv_sec*1e3 + ts.tv_nsec*1e-6;
+}
 
 static const char *Prog_Name = "hetmers";
 
@@ -184,6 +192,7 @@ int main(int argc, char *argv[])
   hm_scan  *S;
   char     *input = NULL;
   int       ngpu, devs[16];
+  double    t_start = wall_ms(), t_open, t_load, t_exam, t_scan;
 
   { char *command, *tname;
     int   symm, trim;
@@ -200,15 +209,19 @@ int main(int argc, char *argv[])
           fprintf(stderr,"%s: %s\n",Prog_Name,hm_last_error());
         exit (1);
       }
+    t_open = wall_ms();
     ngpu = pick_gpus(devs);        /* after the table is known to exist: same first error as the reference */
+    hm_set_io_threads(NTHREADS);   /* -T = host threads staging the part files towards the GPU */
     if (hm_table_view(T)->nels < 2)
       { fprintf(stderr,"%s: k-mer table %s has fewer than 2 entries\n",Prog_Name,SRC);
         exit (1);
       }
     if (hm_scan_create(hm_table_view(T),devs,ngpu,&S) != HM_OK)
       die_hm();
+    t_load = wall_ms();
     if (hm_scan_examine(S,ETHRESH,&trim,&symm) != HM_OK)
       die_hm();
+    t_exam = wall_ms();
 
     if (VERBOSE)
       { fprintf(stderr,"\n  The input table is");
@@ -282,14 +295,17 @@ int main(int argc, char *argv[])
     }
   if (hm_scan_run(S,PLOT,&stats) != HM_OK)
     die_hm();
+  t_scan = wall_ms();
   hm_scan_destroy(S);
   hm_table_close(T);
 
   if (getenv("HETMERS_STATS") != NULL)
     fprintf(stderr,"{\"nels\": %lld, \"n_gpus\": %d, \"bucket_bits\": %d, \"ms_load\": %.3f, "
-                   "\"ms_pass1\": %.3f, \"ms_pass2\": %.3f, \"ms_scan\": %.3f, \"kernel_launches\": %lld}\n",
+                   "\"ms_pass1\": %.3f, \"ms_pass2\": %.3f, \"ms_scan\": %.3f, \"kernel_launches\": %lld, "
+                   "\"wall_ms\": {\"open\": %.1f, \"cuda_init_load\": %.1f, \"examine\": %.1f, \"scan\": %.1f}}\n",
             (long long) stats.nels,stats.n_gpus,stats.bucket_bits,stats.ms_h2d_unpack,
-            stats.ms_pass1,stats.ms_pass2,stats.ms_scan,(long long) stats.kernel_launches);
+            stats.ms_pass1,stats.ms_pass2,stats.ms_scan,(long long) stats.kernel_launches,
+            t_open-t_start,t_load-t_open,t_exam-t_load,t_scan-t_exam);
 
   if (input != NULL)                                              /* PloidyPlot.c:1584-1592 */
     { char *command = malloc(strlen(input)+100);
