@@ -390,7 +390,7 @@ def measure_e2e(args, torch, dist, dev, multi, world, rank, job, tabl):
     L = _lib.lib()
     part_nels = (C.c_int64 * 1)(n)
     part_rec = (C.c_void_p * 1)(h_rec.data_ptr())
-    ht = _lib.HostTable(K, ibyte, 1, LCUT, n, C.cast(h_idx.data_ptr(), C.POINTER(C.c_int64)), part_nels, part_rec)
+    ht = _lib.HostTable(K, ibyte, 1, LCUT, n, C.cast(h_idx.data_ptr(), C.POINTER(C.c_int64)), part_nels, part_rec, None, None)
     devs = (C.c_int * 1)(dev.index or 0)
     plot = torch.empty(_lib.PLOT_CELLS, dtype=torch.int64, pin_memory=True)
     st = _lib.ScanStats()

@@ -155,6 +155,9 @@ typedef struct hm_host_table
     const int64_t  *index;       /* int64[1 << (8*ibyte)] bucket END offsets            */
     const int64_t  *part_nels;   /* [nparts]                                            */
     const uint8_t **part_rec;    /* [nparts] payloads: part_nels[p]*pbyte bytes each    */
+    const int32_t  *part_fd;     /* optional [nparts]: open descriptor of the part file (or -1);  */
+    const int64_t  *part_fd_off; /*   payload starts at this offset.  When given, the loader       */
+                                 /*   pread()s with its host threads instead of touching part_rec  */
   } hm_host_table;
 
 typedef struct hm_scan_stats
@@ -169,6 +172,9 @@ typedef struct hm_scan_stats
     double  ms_scan;             /* pass1 + exchange + pass2 + plot reduce (T_scan)          */
     double  ms_total;            /* wall clock of the call                                   */
     int64_t kernel_launches;     /* kernels of ours launched by the call                     */
+    double  ms_alloc;            /* of ms_h2d_unpack: context + device allocations           */
+    double  ms_records;          /*                   host staging + H2D + unpack            */
+    double  ms_index;            /*                   shard exchange + bucket index + filter */
   } hm_scan_stats;
 
 typedef struct hm_scan hm_scan;   /* opaque: device-resident table + work buffers            */

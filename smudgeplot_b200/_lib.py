@@ -29,7 +29,8 @@ ABI_SYMBOLS = [
 class HostTable(C.Structure):
     _fields_ = [("kmer", C.c_int32), ("ibyte", C.c_int32), ("nparts", C.c_int32), ("minval", C.c_int32),
                 ("nels", C.c_int64), ("index", C.POINTER(C.c_int64)), ("part_nels", C.POINTER(C.c_int64)),
-                ("part_rec", C.POINTER(C.c_void_p))]
+                ("part_rec", C.POINTER(C.c_void_p)), ("part_fd", C.POINTER(C.c_int32)),
+                ("part_fd_off", C.POINTER(C.c_int64))]
 
 
 MAX_SHARDS = 16
@@ -45,7 +46,8 @@ class ScanStats(C.Structure):
     _fields_ = [("nels", C.c_int64), ("n_gpus", C.c_int32), ("bucket_bits", C.c_int32),
                 ("filter_bits", C.c_int32), ("reserved", C.c_int32),
                 ("ms_h2d_unpack", C.c_double), ("ms_pass1", C.c_double), ("ms_pass2", C.c_double),
-                ("ms_scan", C.c_double), ("ms_total", C.c_double), ("kernel_launches", C.c_int64)]
+                ("ms_scan", C.c_double), ("ms_total", C.c_double), ("kernel_launches", C.c_int64),
+                ("ms_alloc", C.c_double), ("ms_records", C.c_double), ("ms_index", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

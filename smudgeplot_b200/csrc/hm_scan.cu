@@ -47,7 +47,7 @@ struct hm_scan
   { int      kmer, ibyte, bits, fpos, idx64, ngpu;
     int64_t  n;
     DevTable d[HM_MAX_GPUS];
-    double   ms_load;
+    double   ms_load, ms_alloc, ms_records, ms_index;
     int64_t  launches;
   };
 
@@ -94,15 +94,27 @@ static int g_io_threads = 0;
 
 extern "C" void hm_set_io_threads(int n) { g_io_threads = n; }
 
-typedef struct { uint8_t *dst; const uint8_t *src; size_t bytes; } CopyJob;
+typedef struct { uint8_t *dst; const uint8_t *src; size_t bytes; int fd; int64_t off; } CopyJob;
 
 static void *copy_worker(void *arg)
 { CopyJob *j = (CopyJob *) arg;
-  memcpy(j->dst,j->src,j->bytes);
+  if (j->fd < 0)
+    memcpy(j->dst,j->src,j->bytes);
+  else
+    { size_t got = 0;                                   /* page cache -> pinned buffer, no mapping */
+      while (got < j->bytes)
+        { ssize_t r = pread(j->fd,j->dst+got,j->bytes-got,j->off+(int64_t) got);
+          if (r <= 0) break;
+          got += (size_t) r;
+        }
+      if (got < j->bytes)
+        memset(j->dst+got,0,j->bytes-got);
+    }
   return NULL;
 }
 
-static void parallel_memcpy(uint8_t *dst, const uint8_t *src, size_t bytes)
+/* fill dst[0,bytes) from memory `src` (fd < 0) or from file `fd` at `off`, with the I/O threads */
+static void parallel_fill(uint8_t *dst, const uint8_t *src, int fd, int64_t foff, size_t bytes)
 { int nt = g_io_threads;
   if (nt <= 0)
     { long c = sysconf(_SC_NPROCESSORS_ONLN);
@@ -117,7 +129,8 @@ static void parallel_memcpy(uint8_t *dst, const uint8_t *src, size_t bytes)
   for (int k = 0; k < nt; k++)
     { size_t off = per*k;
       if (off >= bytes) break;
-      job[k].dst = dst+off; job[k].src = src+off;
+      job[k].dst = dst+off; job[k].src = src ? src+off : NULL;
+      job[k].fd = fd; job[k].off = foff+(int64_t) off;
       job[k].bytes = bytes-off < per ? bytes-off : per;
       if (k == nt-1 || off+per >= bytes)
         { copy_worker(job+k); break; }                 /* the calling thread takes the last slice */
@@ -154,7 +167,8 @@ static int load_range(hm_scan *s, DevTable *D, const hm_host_table *t, const int
   if (count <= 0)
     return HM_OK;
   for (int p = 0; p < t->nparts && !staged; p++)
-    if (t->part_nels[p] > 0 && is_pageable(t->part_rec[p]))
+    if (t->part_nels[p] > 0 &&
+        ((t->part_fd != NULL && t->part_fd[p] >= 0) || is_pageable(t->part_rec[p])))
       staged = 1;
   if (staged)
     chunk = LOAD_CHUNK/2;
@@ -177,7 +191,10 @@ static int load_range(hm_scan *s, DevTable *D, const hm_host_table *t, const int
           if (staged)
             { if (used[b])
                 cudaEventSynchronize(copied[b]);      /* pin[b] has left for the GPU */
-              parallel_memcpy(pin[b],src,(size_t) m*pbyte);
+              if (t->part_fd != NULL && t->part_fd[p] >= 0)
+                parallel_fill(pin[b],NULL,t->part_fd[p],t->part_fd_off[p]+(o-pstart)*pbyte,(size_t) m*pbyte);
+              else
+                parallel_fill(pin[b],src,-1,0,(size_t) m*pbyte);
               src = pin[b];
             }
           if (used[b])
@@ -253,6 +270,7 @@ extern "C" int hm_scan_create(const hm_host_table *t, const int *dev, int n_gpus
 #undef TRY
     }
 
+  double t_alloc = now_ms();
   /* each device unpacks its own shard from the host, then the shards are exchanged over peer
    * copies so that every device ends with the full table                                      */
   for (int g = 0; g < n_gpus && rc == HM_OK; g++)
@@ -266,6 +284,7 @@ extern "C" int hm_scan_create(const hm_host_table *t, const int *dev, int n_gpus
       rc = load_range(s,D,t,d_index,D->lo,D->hi-D->lo);
       cudaFree(d_index);
     }
+  double t_rec = now_ms();
   if (n_gpus > 1 && rc == HM_OK)
     { for (int g = 0; g < n_gpus && rc == HM_OK; g++)        /* all-gather by peer copies */
         for (int h = 0; h < n_gpus && rc == HM_OK; h++)
@@ -300,6 +319,7 @@ extern "C" int hm_scan_create(const hm_host_table *t, const int *dev, int n_gpus
   if (rc != HM_OK)
     { hm_scan_destroy(s); return rc; }
   s->ms_load = now_ms()-t0;
+  s->ms_alloc = t_alloc-t0; s->ms_records = t_rec-t_alloc; s->ms_index = now_ms()-t_rec;
   *out = s;
   return HM_OK;
 }
@@ -476,6 +496,7 @@ extern "C" int hm_scan_run(hm_scan *s, int64_t *plot, hm_scan_stats *stats)
       stats->ms_scan = G > 1 ? (t1-t0) : msall;
       stats->ms_total = s->ms_load + (t1-t0);
       stats->kernel_launches = s->launches;
+      stats->ms_alloc = s->ms_alloc; stats->ms_records = s->ms_records; stats->ms_index = s->ms_index;
     }
   (void) launches0;
   return HM_OK;

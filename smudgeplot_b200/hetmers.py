@@ -69,7 +69,7 @@ def _host_table(kt: KtabFiles):
     part_nels = (C.c_int64 * max(nparts, 1))(*[int(x) for x in kt.part_nels])
     part_rec = (C.c_void_p * max(nparts, 1))(*[r.ctypes.data if r.size else None for r in recs])
     ht = _lib.HostTable(kt.kmer, kt.ibyte, nparts, kt.minval, kt.nels,
-                        index.ctypes.data_as(C.POINTER(C.c_int64)), part_nels, part_rec)
+                        index.ctypes.data_as(C.POINTER(C.c_int64)), part_nels, part_rec, None, None)
     return ht, (index, recs, part_nels, part_rec)
 
 

@@ -32,6 +32,8 @@ struct hm_table
     const uint8_t **part_rec;
     void          **map_base;
     size_t         *map_len;
+    int32_t        *part_fd;
+    int64_t        *part_fd_off;
   };
 
 /* dir and root of <name> as PathTo()/Root(name,".ktab") give them (gene_core.c:64-114) */
@@ -60,7 +62,11 @@ void hm_table_close(hm_table *t)
     for (p = 0; p < t->view.nparts; p++)
       if (t->map_base[p] != NULL)
         munmap(t->map_base[p],t->map_len[p]);
-  free(t->map_base); free(t->map_len);
+  if (t->part_fd != NULL)
+    for (p = 0; p < t->view.nparts; p++)
+      if (t->part_fd[p] >= 0)
+        close(t->part_fd[p]);
+  free(t->map_base); free(t->map_len); free(t->part_fd); free(t->part_fd_off);
   free(t->index); free(t->part_nels); free((void *) t->part_rec);
   free(t);
 }
@@ -121,10 +127,18 @@ int hm_table_open(const char *name, hm_table **out)
   t->part_rec  = calloc((size_t) hdr[1]+1,sizeof(uint8_t *));
   t->map_base  = calloc((size_t) hdr[1]+1,sizeof(void *));
   t->map_len   = calloc((size_t) hdr[1]+1,sizeof(size_t));
-  if (t->part_nels == NULL || t->part_rec == NULL || t->map_base == NULL || t->map_len == NULL)
+  t->part_fd     = malloc(((size_t) hdr[1]+1)*sizeof(int32_t));
+  t->part_fd_off = calloc((size_t) hdr[1]+1,sizeof(int64_t));
+  if (t->part_fd != NULL)
+    for (p = 0; p <= hdr[1]; p++)
+      t->part_fd[p] = -1;
+  if (t->part_nels == NULL || t->part_rec == NULL || t->map_base == NULL || t->map_len == NULL ||
+      t->part_fd == NULL || t->part_fd_off == NULL)
     { rc = hm_set_error(HM_ENOMEM,"Out of memory (Allocating parts table)"); goto fail; }
-  t->view.part_nels = t->part_nels;
-  t->view.part_rec  = t->part_rec;
+  t->view.part_nels   = t->part_nels;
+  t->view.part_rec    = t->part_rec;
+  t->view.part_fd     = t->part_fd;
+  t->view.part_fd_off = t->part_fd_off;
 
   nels = 0;
   for (p = 1; p <= hdr[1]; p++)
@@ -153,12 +167,14 @@ int hm_table_open(const char *name, hm_table **out)
           m = mmap(NULL,len,PROT_READ,MAP_PRIVATE,f,0);
           if (m == MAP_FAILED)
             { close(f); rc = hm_set_error(HM_EIO,"cannot map %s: %s",path,strerror(errno)); goto fail; }
-          madvise(m,len,MADV_SEQUENTIAL|MADV_WILLNEED);
           t->map_base[p-1] = m;
           t->map_len[p-1]  = len;
           t->part_rec[p-1] = ((const uint8_t *) m)+PART_HEADER;
+          t->part_fd[p-1]     = f;               /* kept open: the GPU loader pread()s the payload */
+          t->part_fd_off[p-1] = PART_HEADER;
         }
-      close(f);
+      else
+        close(f);
       t->part_nels[p-1] = n;
       nels += n;
     }
