@@ -34,7 +34,7 @@ extern "C" {
 #define HM_FMAX         500                 /* max min(CovA,CovB) (PloidyPlot.c:49) */
 #define HM_PLOT_W      (HM_FMAX+1)
 #define HM_PLOT_CELLS  ((HM_SMAX+1)*(HM_FMAX+1))   /* int64 plot[1001][501] (PloidyPlot.c:1466-1473) */
-#define HM_MAX_KMER      32                 /* one 64-bit word per packed k-mer (this round) */
+#define HM_MAX_KMER      64                 /* 1 (k<=32) or 2 (k<=64) 64-bit words per packed k-mer */
 #define HM_MAX_SHARDS    16                 /* GPUs one table can be sharded over           */
 #define HM_FILTER_MIN_BITS 22               /* prefix-filter width in bits                  */
 #define HM_FILTER_MAX_BITS 37
@@ -58,6 +58,7 @@ int         hm_device_info(int dev, char *name, int name_len, int *sm_count, int
  * Device table layout (structure of arrays):
  *   keys  uint64[n]  packed 2-bit k-mer, LEFT aligned (base i in bits 63-2i..62-2i), ascending;
  *                    uint64 order == FastK table order (libfastk.c packing :571-579)
+ *   keys_lo uint64[n] bases 32..63 (left aligned) when k > 32, else NULL: order = (keys, keys_lo)
  *   cnt   uint16[n]  k-mer counts
  *   deg   uint8 [n]  incidence array == the reference's `Pair` (PloidyPlot.c:163), allocated
  *                    with size rounded up to a multiple of 4 and 4-byte aligned
@@ -71,7 +72,7 @@ int         hm_device_info(int dev, char *name, int name_len, int *sm_count, int
  * holding table ordinals [first, first+n); d_stub_index: int64[1<<(8*ibyte)] on the device.   */
 int hm_k_unpack_records(const uint8_t *d_rec, int64_t n, int64_t first,
                         const int64_t *d_stub_index, int ibyte, int kmer,
-                        uint64_t *d_keys, uint16_t *d_cnt, void *stream);
+                        uint64_t *d_keys, uint64_t *d_keys_lo, uint16_t *d_cnt, void *stream);
 
 /* Prefix (bucket) index over the sorted keys; takes the place of the stub index + on-disk
  * bisection of GoTo_Kmer_Entry (libfastk.c:1320-1409).                                        */
@@ -108,7 +109,8 @@ typedef struct hm_shards
  * deg[y] (mod 256, atomically) and remember the pair's upper member in d_up[x-lo]
  * (all-ones = none; d_up is initialised here).  d_deg must be zeroed by the caller before the
  * first call (several ranges / GPUs accumulate into it).                                      */
-int hm_k_pass1_degree(const uint64_t *d_keys, const uint16_t *d_cnt, int64_t n,
+int hm_k_pass1_degree(const uint64_t *d_keys, const uint64_t *d_keys_lo,
+                      const uint16_t *d_cnt, int64_t n,
                       const void *d_bucket, int bits, int idx64,
                       const uint32_t *d_filter, int filter_bits, int kmer,
                       int64_t lo, int64_t hi, uint8_t *d_deg, void *d_up,
@@ -138,8 +140,10 @@ int hm_k_min_count(const uint16_t *d_cnt, int64_t frst, int64_t last, int *d_min
 
 /* exact-match lookup of nq packed k-mers: d_pos[q] = table index or -1.  Replaces
  * GoTo_Kmer_Entry's "return 1 iff exact hit" use (libfastk.c:1320-1409; PloidyPlot.c:1213). */
-int hm_k_find_keys(const uint64_t *d_keys, int64_t n, const void *d_bucket, int bits, int idx64,
-                   const uint64_t *d_query, int64_t nq, int64_t *d_pos, void *stream);
+int hm_k_find_keys(const uint64_t *d_keys, const uint64_t *d_keys_lo, int64_t n,
+                   const void *d_bucket, int bits, int idx64,
+                   const uint64_t *d_query, const uint64_t *d_query_lo, int64_t nq,
+                   int64_t *d_pos, void *stream);
 
 /* choice of bucket-index width for a table of n entries */
 int hm_pick_bucket_bits(int64_t n);
@@ -195,7 +199,7 @@ int  hm_scan_run(hm_scan *s, int64_t *plot, hm_scan_stats *stats);
 int  hm_hetmers_host(const hm_host_table *t, const int *dev, int n_gpus,
                      int64_t *plot, hm_scan_stats *stats);
 /* copy device arrays back for tests: any pointer may be NULL */
-int  hm_scan_download(hm_scan *s, uint64_t *keys, uint16_t *cnt, uint8_t *deg);
+int  hm_scan_download(hm_scan *s, uint64_t *keys, uint64_t *keys_lo, uint16_t *cnt, uint8_t *deg);
 
 /* ======================= C. FastK table files (host, plain C) ============================ */
 

@@ -74,9 +74,9 @@ def lib():
     vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
     L.hm_last_error.restype = C.c_char_p
     L.hm_device_info.argtypes = [i32, C.c_char_p, i32, C.POINTER(i32), C.POINTER(i64)]
-    L.hm_k_unpack_records.argtypes = [vp, i64, i64, vp, i32, i32, vp, vp, vp]
+    L.hm_k_unpack_records.argtypes = [vp, i64, i64, vp, i32, i32, vp, vp, vp, vp]
     L.hm_k_build_bucket_index.argtypes = [vp, i64, i32, vp, i32, vp]
-    L.hm_k_pass1_degree.argtypes = [vp, vp, i64, vp, i32, i32, vp, i32, i32, i64, i64, vp, vp, C.POINTER(Shards), vp]
+    L.hm_k_pass1_degree.argtypes = [vp, vp, vp, i64, vp, i32, i32, vp, i32, i32, i64, i64, vp, vp, C.POINTER(Shards), vp]
     L.hm_dev_alloc.argtypes = [i64, C.POINTER(vp)]
     L.hm_dev_free.argtypes = [vp]
     L.hm_ipc_export.argtypes = [vp, C.c_char_p]
@@ -89,7 +89,7 @@ def lib():
     L.hm_pick_filter_bits.argtypes = [i64]
     L.hm_k_pass2_plot.argtypes = [vp, vp, vp, i32, i64, i64, vp, C.POINTER(Shards), vp]
     L.hm_k_min_count.argtypes = [vp, i64, i64, vp, vp]
-    L.hm_k_find_keys.argtypes = [vp, i64, vp, i32, i32, vp, i64, vp, vp]
+    L.hm_k_find_keys.argtypes = [vp, vp, i64, vp, i32, i32, vp, vp, i64, vp, vp]
     L.hm_pick_bucket_bits.argtypes = [i64]
     L.hm_scan_create.argtypes = [C.POINTER(HostTable), C.POINTER(i32), i32, C.POINTER(vp)]
     L.hm_scan_destroy.argtypes = [vp]
@@ -97,7 +97,7 @@ def lib():
     L.hm_scan_examine.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
     L.hm_scan_run.argtypes = [vp, vp, C.POINTER(ScanStats)]
     L.hm_hetmers_host.argtypes = [C.POINTER(HostTable), C.POINTER(i32), i32, vp, C.POINTER(ScanStats)]
-    L.hm_scan_download.argtypes = [vp, vp, vp, vp]
+    L.hm_scan_download.argtypes = [vp, vp, vp, vp, vp]
     L.hm_table_open.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.hm_table_close.argtypes = [vp]
     L.hm_table_close.restype = None

@@ -72,20 +72,33 @@ extern "C" int hm_pick_bucket_bits(int64_t n)
 
 template <typename IdxT> struct IdxNone { static constexpr IdxT value = (IdxT) ~(IdxT) 0; };
 
-/* exact match of y inside its prefix bucket; -1 if absent */
-template <typename IdxT>
+/* exact match of y inside its prefix bucket; -1 if absent.  KW = 64-bit words per key (k <= 32: 1,
+ * k <= 64: 2, second word in the parallel array keys_lo); buckets are prefixes of the first word. */
+template <typename IdxT, int KW>
 __device__ __forceinline__ int64_t bucket_find(const uint64_t *__restrict__ keys,
+                                               const uint64_t *__restrict__ keys_lo,
                                                const IdxT *__restrict__ bucket,
-                                               int bshift, uint64_t y)
+                                               int bshift, uint64_t y, uint64_t ylo)
 { uint64_t bk = y >> bshift;
   IdxT l = bucket[bk];
   IdxT r = bucket[bk+1];
   while (l < r)
     { IdxT     m = l + ((r-l)>>1);
       uint64_t v = __ldg(keys+m);
-      if (v == y)
-        return (int64_t) m;
-      if (v < y) l = m+1; else r = m;
+      if (KW == 1)
+        { if (v == y)
+            return (int64_t) m;
+          if (v < y) l = m+1; else r = m;
+        }
+      else
+        { if (v == y)
+            { uint64_t w = __ldg(keys_lo+m);
+              if (w == ylo)
+                return (int64_t) m;
+              if (w < ylo) l = m+1; else r = m;
+            }
+          else if (v < y) l = m+1; else r = m;
+        }
     }
   return -1;
 }
@@ -105,7 +118,8 @@ __device__ __forceinline__ int upper_bound_index(const int64_t *__restrict__ ind
 __global__ void __launch_bounds__(256)
 unpack_records_kernel(const uint8_t *__restrict__ rec, int64_t n, int64_t first,
                       const int64_t *__restrict__ index, int ixlen, int ibyte, int hbyte,
-                      uint64_t *__restrict__ keys, uint16_t *__restrict__ cnt)
+                      uint64_t *__restrict__ keys, uint64_t *__restrict__ keys_lo,
+                      uint16_t *__restrict__ cnt)
 { __shared__ int s_blo, s_bhi;
   int64_t t0 = (int64_t) blockIdx.x * blockDim.x;
   if (threadIdx.x == 0)
@@ -121,13 +135,15 @@ unpack_records_kernel(const uint8_t *__restrict__ rec, int64_t n, int64_t first,
   int pbyte = hbyte+2;
   uint64_t b = (uint64_t) upper_bound_index(index,s_blo,s_bhi,first+i);
   const uint8_t *r = rec + i*pbyte;
-  uint64_t v = 0;
-  for (int j = 0; j < hbyte; j++)
-    v = (v<<8) | r[j];
-  uint64_t key = b << (64-8*ibyte);
-  if (hbyte > 0)
-    key |= v << (64-8*(ibyte+hbyte));
+  uint64_t key = b << (64-8*ibyte), klo = 0;
+  for (int j = 0; j < hbyte; j++)                     /* suffix byte j is key byte ibyte+j */
+    { int pos = ibyte+j;
+      if (pos < 8) key |= (uint64_t) r[j] << (56-8*pos);
+      else         klo |= (uint64_t) r[j] << (56-8*(pos-8));
+    }
   keys[i] = key;
+  if (keys_lo != NULL)
+    keys_lo[i] = klo;
   cnt[i]  = (uint16_t) (r[hbyte] | (r[hbyte+1]<<8));
 }
 
@@ -169,7 +185,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
 __global__ void __launch_bounds__(256)
 unpack_records_tma_kernel(const uint8_t *__restrict__ rec, int64_t first,
                           const int64_t *__restrict__ index, int ixlen, int ibyte, int hbyte,
-                          uint64_t *__restrict__ keys, uint16_t *__restrict__ cnt)
+                          uint64_t *__restrict__ keys, uint64_t *__restrict__ keys_lo,
+                          uint16_t *__restrict__ cnt)
 { extern __shared__ __align__(128) uint8_t s_rec[];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_blo, s_bhi;
@@ -198,25 +215,30 @@ unpack_records_tma_kernel(const uint8_t *__restrict__ rec, int64_t first,
       const int64_t  i = t0+r;
       const uint8_t *q = s_rec + r*pbyte;
       uint64_t b = (uint64_t) upper_bound_index(index,blo,bhi,first+i);
-      uint64_t v = 0;
+      uint64_t key = b << (64-8*ibyte), klo = 0;
       for (int j = 0; j < hbyte; j++)
-        v = (v<<8) | q[j];
-      uint64_t key = b << (64-8*ibyte);
-      if (hbyte > 0)
-        key |= v << (64-8*(ibyte+hbyte));
+        { int pos = ibyte+j;
+          if (pos < 8) key |= (uint64_t) q[j] << (56-8*pos);
+          else         klo |= (uint64_t) q[j] << (56-8*(pos-8));
+        }
       keys[i] = key;
+      if (keys_lo != NULL)
+        keys_lo[i] = klo;
       cnt[i]  = (uint16_t) (q[hbyte] | (q[hbyte+1]<<8));
     }
 }
 
 extern "C" int hm_k_unpack_records(const uint8_t *d_rec, int64_t n, int64_t first,
                                    const int64_t *d_stub_index, int ibyte, int kmer,
-                                   uint64_t *d_keys, uint16_t *d_cnt, void *stream)
+                                   uint64_t *d_keys, uint64_t *d_keys_lo, uint16_t *d_cnt, void *stream)
 { if (kmer < 1 || kmer > HM_MAX_KMER)
     return hm_set_error(HM_EUNSUPPORTED,"k-mer length %d not supported (1..%d)",kmer,HM_MAX_KMER);
   int kbyte = (kmer+3)>>2;
   if (ibyte < 1 || ibyte > 3 || ibyte > kbyte)
     return hm_set_error(HM_EFORMAT,"prefix bytes ibyte=%d invalid for k=%d",ibyte,kmer);
+  if ((kmer > 32) != (d_keys_lo != NULL))
+    return hm_set_error(HM_EINVAL,"unpack: second key word array %s for k=%d",
+                        d_keys_lo ? "given" : "missing",kmer);
   if (n <= 0)
     return HM_OK;
   int     hbyte = kbyte-ibyte, pbyte = hbyte+2;
@@ -224,7 +246,7 @@ extern "C" int hm_k_unpack_records(const uint8_t *d_rec, int64_t n, int64_t firs
   if ((((uintptr_t) d_rec) & 15) == 0 && n >= UNP_TILE)         /* full tiles through the TMA path */
     { int64_t ntiles = n/UNP_TILE;
       unpack_records_tma_kernel<<<(unsigned) ntiles,256,(size_t) UNP_TILE*pbyte,(cudaStream_t) stream>>>
-          (d_rec,first,d_stub_index,1<<(8*ibyte),ibyte,hbyte,d_keys,d_cnt);
+          (d_rec,first,d_stub_index,1<<(8*ibyte),ibyte,hbyte,d_keys,d_keys_lo,d_cnt);
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess)
         return hm_cuda_fail(e,"unpack_records_tma_kernel");
@@ -234,7 +256,8 @@ extern "C" int hm_k_unpack_records(const uint8_t *d_rec, int64_t n, int64_t firs
     { int64_t m = n-done;
       int64_t nblk = (m+255)/256;
       unpack_records_kernel<<<(unsigned) nblk,256,0,(cudaStream_t) stream>>>
-          (d_rec + done*pbyte,m,first+done,d_stub_index,1<<(8*ibyte),ibyte,hbyte,d_keys+done,d_cnt+done);
+          (d_rec + done*pbyte,m,first+done,d_stub_index,1<<(8*ibyte),ibyte,hbyte,d_keys+done,
+           d_keys_lo ? d_keys_lo+done : NULL,d_cnt+done);
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess)
         return hm_cuda_fail(e,"unpack_records_kernel");
@@ -403,23 +426,27 @@ __device__ __forceinline__ void book_pair(const uint16_t *__restrict__ cnt, int6
  *   survivors are expanded into a per-warp shared-memory queue and resolved 32 at a time by a
  *        bucket lookup + bisection with every lane busy (the expensive, divergent part of the
  *        search runs at full SIMT efficiency and only for ~1 candidate per entry).            */
-template <typename IdxT, int F>
+template <typename IdxT, int F, int KW>
 __global__ void __launch_bounds__(P1_WARPS*32,P1_MINBLOCKS)
-pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restrict__ cnt,
+pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ keys_lo,
+                    const uint16_t *__restrict__ cnt,
                     int64_t n, const IdxT *__restrict__ bucket, int bshift,
                     const uint32_t *__restrict__ filter, int kmer,
                     int64_t lo, int64_t hi, const DegView dv, IdxT *__restrict__ up)
 { __shared__ uint64_t s_qy[P1_WARPS][P1_QCAP];
+  __shared__ uint64_t s_ql[KW == 2 ? P1_WARPS : 1][KW == 2 ? P1_QCAP : 1];
   __shared__ IdxT     s_qi[P1_WARPS][P1_QCAP];
 
   constexpr int PH  = (F+1)/2;                              /* positions with a bit in the prefix */
   constexpr int NA  = PH < 9 ? PH : 9;
   constexpr int SFT = F > 32 ? F-32 : 0;                    /* filter bits taken from the low word */
+  constexpr int MW  = KW == 2 ? 3 : 1;                      /* words of the long-run fallback mask */
   const unsigned FULL = 0xffffffffu;
   const int      lane = threadIdx.x & 31;
   const int      warp = threadIdx.x >> 5;
   const unsigned lt   = (1u << lane) - 1;
   uint64_t *qy = s_qy[warp];
+  uint64_t *ql = s_ql[KW == 2 ? warp : 0];
   IdxT     *qi = s_qi[warp];
   int       qn = 0;                                      /* warp-uniform queue fill */
 
@@ -428,13 +455,18 @@ pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restric
        c += (int64_t) gridDim.x * P1_WARPS)
     { const int64_t i = lo + (c<<5) + lane;
       const bool    valid = (i < hi);
-      uint64_t x = 0, nxt = 0;
+      uint64_t x = 0, nxt = 0, xw = 0, nxtw = 0;         /* xw / nxtw: second key word (KW == 2) */
       int      pmax = -1;
       if (valid)
         { x = keys[i];
+          if (KW == 2) xw = keys_lo[i];
           if (i+1 < n)
-            { nxt  = keys[i+1];
-              pmax = __clzll((long long) (x ^ nxt)) >> 1;
+            { nxt = keys[i+1];
+              if (KW == 2) nxtw = keys_lo[i+1];
+              if (KW == 1 || x != nxt)
+                pmax = __clzll((long long) (x ^ nxt)) >> 1;
+              else
+                pmax = 32 + (__clzll((long long) (xw ^ nxtw)) >> 1);
               if (pmax > kmer-1) pmax = kmer-1;
             }
         }
@@ -453,7 +485,7 @@ pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restric
           for (int c = 1; c <= 3; c++)
             { bool     act;
               uint32_t widx, bit;
-              if (p < 16)                                    /* base p lives in the high word */
+              if (p < 16)                                    /* base p lives in the high half */
                 { const int      s  = 30-2*p;
                   const uint32_t yh = (xh & ~(3u << s)) | ((uint32_t) c << s);
                   act = pa && (yh > xh);
@@ -466,7 +498,7 @@ pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restric
                       bit  = ((yh << SFT) | (xl >> (32-SFT))) & 31;
                     }
                 }
-              else                                           /* F > 32: base p in the low word */
+              else                                           /* F > 32: base p in the low half */
                 { const int      s  = 62-2*p;
                   const uint32_t yl = (xl & ~(3u << s)) | ((uint32_t) c << s);
                   act  = pa && (yl > xl);
@@ -483,65 +515,97 @@ pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restric
         }
 
       /* ---- high positions: the run of entries sharing x's PH-base prefix ---- */
-      uint64_t mhi = 0;
+      uint64_t mhi[MW];
+#pragma unroll
+      for (int w = 0; w < MW; w++)
+        mhi[w] = 0;
       if (pmax >= PH)
         { bool longrun = (i+P1_RUNCAP < n) &&
                          (((x ^ __ldg(keys+i+P1_RUNCAP)) >> (64-2*PH)) == 0);
           if (longrun)
             { for (int p = PH; p <= pmax; p++)
-                { int b = (int) ((x >> (62-2*p)) & 3);
-                  for (int c = b+1; c <= 3; c++)
-                    mhi |= (uint64_t) 1 << (3*(p-PH)+c-1);
+                { int b = (int) (((p < 32 ? x : xw) >> (62-2*(p&31))) & 3);
+                  for (int cc = b+1; cc <= 3; cc++)
+                    { int t = 3*(p-PH)+cc-1;
+#pragma unroll
+                      for (int w = 0; w < MW; w++)
+                        if ((t>>6) == w)
+                          mhi[w] |= (uint64_t) 1 << (t&63);
+                    }
                 }
             }
           else
             { int64_t  j = i+1;
-              uint64_t z = nxt;
+              uint64_t z = nxt, zw = nxtw;
               while (true)
                 { uint64_t dd = x ^ z;
                   if ((dd >> (64-2*PH)) != 0)
                     break;
                   uint64_t t = (dd | (dd>>1)) & 0x5555555555555555ull;
-                  if ((t & (t-1)) == 0)                    /* exactly one base differs */
+                  bool one = ((t & (t-1)) == 0);           /* at most one base of word 0 differs */
+                  if (KW == 2)
+                    { uint64_t dw = xw ^ zw;
+                      uint64_t u  = (dw | (dw>>1)) & 0x5555555555555555ull;
+                      one = one && ((u & (u-1)) == 0) && ((t == 0) != (u == 0));
+                    }
+                  if (one)                                  /* exactly one base differs */
                     book_pair<IdxT>(cnt,i,j,lo,dv,up);
                   j += 1;
                   if (j >= n)
                     break;
                   z = __ldg(keys+j);
+                  if (KW == 2) zw = __ldg(keys_lo+j);
                 }
             }
         }
 
       /* ---- expand survivors into the warp queue; resolve 32 at a time ---- */
-      while (__any_sync(FULL,(ma | mb | mhi) != 0))
-        { const bool has = (ma | mb | mhi) != 0;
-          uint64_t   y = 0;
+      while (true)
+        { uint64_t anyhi = mhi[0];
+#pragma unroll
+          for (int w = 1; w < MW; w++)
+            anyhi |= mhi[w];
+          const bool has = ((ma | mb) != 0) || (anyhi != 0);
+          if (!__any_sync(FULL,has))
+            break;
+          uint64_t y = x, yw = xw;
           if (has)
-            { int p, c;
+            { int p, cc;
               if (ma != 0)
                 { int t = 31-__clz((int) ma);
                   ma &= ~(1u << t);
                   int q = 3*NA-1-t;
-                  p = q/3; c = q-3*p+1;
+                  p = q/3; cc = q-3*p+1;
                 }
               else if (mb != 0)
                 { int t = 31-__clz((int) mb);
                   mb &= ~(1u << t);
                   int q = 3*(PH-NA)-1-t;
-                  p = q/3; c = q-3*p+1; p += NA;
+                  p = q/3; cc = q-3*p+1; p += NA;
                 }
               else
-                { int t = __ffsll((long long) mhi)-1;
-                  mhi &= mhi-1;
-                  p = t/3; c = t-3*p+1; p += PH;
+                { int t = 0;
+#pragma unroll
+                  for (int w = MW-1; w >= 0; w--)
+                    if (mhi[w] != 0)
+                      t = 64*w + __ffsll((long long) mhi[w])-1;
+#pragma unroll
+                  for (int w = 0; w < MW; w++)
+                    if ((t>>6) == w)
+                      mhi[w] &= mhi[w]-1;
+                  p = t/3; cc = t-3*p+1; p += PH;
                 }
-              const int sh = 62-2*p;
-              y = (x & ~((uint64_t) 3 << sh)) | ((uint64_t) c << sh);
+              const int sh = 62-2*(p&31);
+              if (KW == 1 || p < 32)
+                y = (x & ~((uint64_t) 3 << sh)) | ((uint64_t) cc << sh);
+              else
+                yw = (xw & ~((uint64_t) 3 << sh)) | ((uint64_t) cc << sh);
             }
           const unsigned bal = __ballot_sync(FULL,has);
           if (has)
             { int pos = qn + __popc(bal & lt);
               qy[pos] = y;
+              if (KW == 2) ql[pos] = yw;
               qi[pos] = (IdxT) i;
             }
           qn += __popc(bal);
@@ -549,9 +613,10 @@ pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restric
           if (qn >= 32)
             { qn -= 32;
               uint64_t yy = qy[qn+lane];
+              uint64_t yl = KW == 2 ? ql[qn+lane] : 0;
               int64_t  oi = (int64_t) qi[qn+lane];
               __syncwarp();
-              int64_t j = bucket_find<IdxT>(keys,bucket,bshift,yy);
+              int64_t j = bucket_find<IdxT,KW>(keys,keys_lo,bucket,bshift,yy,yl);
               if (j >= 0)
                 book_pair<IdxT>(cnt,oi,j,lo,dv,up);
             }
@@ -560,15 +625,16 @@ pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint16_t *__restric
 
   if (lane < qn)                                          /* left-overs */
     { uint64_t yy = qy[lane];
+      uint64_t yl = KW == 2 ? ql[lane] : 0;
       int64_t  oi = (int64_t) qi[lane];
-      int64_t  j  = bucket_find<IdxT>(keys,bucket,bshift,yy);
+      int64_t  j  = bucket_find<IdxT,KW>(keys,keys_lo,bucket,bshift,yy,yl);
       if (j >= 0)
         book_pair<IdxT>(cnt,oi,j,lo,dv,up);
     }
 }
 
-template <typename IdxT, int F>
-static cudaError_t launch_pass1(const uint64_t *keys, const uint16_t *cnt, int64_t n,
+template <typename IdxT, int F, int KW>
+static cudaError_t launch_pass1(const uint64_t *keys, const uint64_t *keys_lo, const uint16_t *cnt, int64_t n,
                                 const void *bucket, int bits, const uint32_t *filter, int kmer,
                                 int64_t lo, int64_t hi, const DegView &dv, void *up, cudaStream_t st)
 { int dev = 0, sms = 148;
@@ -578,18 +644,19 @@ static cudaError_t launch_pass1(const uint64_t *keys, const uint16_t *cnt, int64
   int64_t want    = (nchunks+P1_WARPS-1)/P1_WARPS;
   int64_t cap     = (int64_t) sms*8*4;            /* 4 waves of 8 resident CTAs per SM */
   int     grid    = (int) (want < cap ? want : cap);
-  pass1_filter_kernel<IdxT,F><<<grid,P1_WARPS*32,0,st>>>
-      (keys,cnt,n,(const IdxT *) bucket,64-bits,filter,kmer,lo,hi,dv,(IdxT *) up);
+  pass1_filter_kernel<IdxT,F,KW><<<grid,P1_WARPS*32,0,st>>>
+      (keys,keys_lo,cnt,n,(const IdxT *) bucket,64-bits,filter,kmer,lo,hi,dv,(IdxT *) up);
   return cudaGetLastError();
 }
 
-template <typename IdxT>
-static cudaError_t dispatch_pass1(int fb, const uint64_t *keys, const uint16_t *cnt, int64_t n,
+template <typename IdxT, int KW>
+static cudaError_t dispatch_pass1(int fb, const uint64_t *keys, const uint64_t *keys_lo,
+                                  const uint16_t *cnt, int64_t n,
                                   const void *bucket, int bits, const uint32_t *filter, int kmer,
                                   int64_t lo, int64_t hi, const DegView &dv, void *up, cudaStream_t st)
 { switch (fb)
   {
-#define CASE(P) case P: return launch_pass1<IdxT,P>(keys,cnt,n,bucket,bits,filter,kmer,lo,hi,dv,up,st);
+#define CASE(P) case P: return launch_pass1<IdxT,P,KW>(keys,keys_lo,cnt,n,bucket,bits,filter,kmer,lo,hi,dv,up,st);
     CASE(22) CASE(23) CASE(24) CASE(25) CASE(26) CASE(27) CASE(28) CASE(29)
     CASE(30) CASE(31) CASE(32) CASE(33) CASE(34) CASE(35) CASE(36) CASE(37)
 #undef CASE
@@ -597,7 +664,8 @@ static cudaError_t dispatch_pass1(int fb, const uint64_t *keys, const uint16_t *
   return cudaErrorInvalidValue;
 }
 
-extern "C" int hm_k_pass1_degree(const uint64_t *d_keys, const uint16_t *d_cnt, int64_t n,
+extern "C" int hm_k_pass1_degree(const uint64_t *d_keys, const uint64_t *d_keys_lo,
+                                 const uint16_t *d_cnt, int64_t n,
                                  const void *d_bucket, int bits, int idx64,
                                  const uint32_t *d_filter, int filter_bits, int kmer,
                                  int64_t lo, int64_t hi, uint8_t *d_deg, void *d_up,
@@ -609,6 +677,9 @@ extern "C" int hm_k_pass1_degree(const uint64_t *d_keys, const uint16_t *d_cnt, 
                         (long long) lo,(long long) hi,(long long) n,bits);
   if (filter_bits < HM_FILTER_MIN_BITS || filter_bits > HM_FILTER_MAX_BITS)
     return hm_set_error(HM_EINVAL,"pass1: filter bits %d out of range",filter_bits);
+  if ((kmer > 32) != (d_keys_lo != NULL))
+    return hm_set_error(HM_EINVAL,"pass1: second key word array %s for k=%d",
+                        d_keys_lo ? "given" : "missing",kmer);
   if (hi == lo)
     return HM_OK;
   if (shards != NULL && shards->n_shards > 1 &&
@@ -618,9 +689,15 @@ extern "C" int hm_k_pass1_degree(const uint64_t *d_keys, const uint16_t *d_cnt, 
   cudaStream_t st = (cudaStream_t) stream;
   DegView dv = make_deg_view(d_deg,lo,hi,shards);
   HM_CUDA(cudaMemsetAsync(d_up,0xFF,(idx64 ? 8 : 4)*(size_t) (hi-lo),st));   /* all-ones = none */
-  cudaError_t e = idx64
-      ? dispatch_pass1<uint64_t>(filter_bits,d_keys,d_cnt,n,d_bucket,bits,d_filter,kmer,lo,hi,dv,d_up,st)
-      : dispatch_pass1<uint32_t>(filter_bits,d_keys,d_cnt,n,d_bucket,bits,d_filter,kmer,lo,hi,dv,d_up,st);
+  cudaError_t e;
+  if (kmer <= 32)
+    e = idx64
+      ? dispatch_pass1<uint64_t,1>(filter_bits,d_keys,NULL,d_cnt,n,d_bucket,bits,d_filter,kmer,lo,hi,dv,d_up,st)
+      : dispatch_pass1<uint32_t,1>(filter_bits,d_keys,NULL,d_cnt,n,d_bucket,bits,d_filter,kmer,lo,hi,dv,d_up,st);
+  else
+    e = idx64
+      ? dispatch_pass1<uint64_t,2>(filter_bits,d_keys,d_keys_lo,d_cnt,n,d_bucket,bits,d_filter,kmer,lo,hi,dv,d_up,st)
+      : dispatch_pass1<uint32_t,2>(filter_bits,d_keys,d_keys_lo,d_cnt,n,d_bucket,bits,d_filter,kmer,lo,hi,dv,d_up,st);
   if (e != cudaSuccess)
     return hm_cuda_fail(e,"pass1_filter_kernel");
   return HM_OK;
@@ -738,28 +815,41 @@ extern "C" int hm_k_min_count(const uint16_t *d_cnt, int64_t frst, int64_t last,
   return HM_OK;
 }
 
-template <typename IdxT>
+template <typename IdxT, int KW>
 __global__ void __launch_bounds__(128)
-find_keys_kernel(const uint64_t *__restrict__ keys, const IdxT *__restrict__ bucket, int bshift,
-                 const uint64_t *__restrict__ query, int64_t nq, int64_t *__restrict__ pos)
+find_keys_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ keys_lo,
+                 const IdxT *__restrict__ bucket, int bshift,
+                 const uint64_t *__restrict__ query, const uint64_t *__restrict__ query_lo,
+                 int64_t nq, int64_t *__restrict__ pos)
 { int64_t q = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (q < nq)
-    pos[q] = bucket_find<IdxT>(keys,bucket,bshift,query[q]);
+    pos[q] = bucket_find<IdxT,KW>(keys,keys_lo,bucket,bshift,query[q],KW == 2 ? query_lo[q] : 0);
 }
 
-extern "C" int hm_k_find_keys(const uint64_t *d_keys, int64_t n, const void *d_bucket, int bits,
-                              int idx64, const uint64_t *d_query, int64_t nq, int64_t *d_pos,
-                              void *stream)
+extern "C" int hm_k_find_keys(const uint64_t *d_keys, const uint64_t *d_keys_lo, int64_t n,
+                              const void *d_bucket, int bits, int idx64,
+                              const uint64_t *d_query, const uint64_t *d_query_lo, int64_t nq,
+                              int64_t *d_pos, void *stream)
 { (void) n;
   if (nq <= 0)
     return HM_OK;
-  int64_t nblk = (nq+127)/128;
-  if (idx64)
-    find_keys_kernel<uint64_t><<<(unsigned) nblk,128,0,(cudaStream_t) stream>>>
-        (d_keys,(const uint64_t *) d_bucket,64-bits,d_query,nq,d_pos);
+  if ((d_keys_lo != NULL) != (d_query_lo != NULL))
+    return hm_set_error(HM_EINVAL,"find_keys: table and queries must have the same number of key words");
+  int64_t      nblk = (nq+127)/128;
+  cudaStream_t st = (cudaStream_t) stream;
+  int          sh = 64-bits;
+  if (d_keys_lo == NULL)
+    { if (idx64)
+        find_keys_kernel<uint64_t,1><<<(unsigned) nblk,128,0,st>>>(d_keys,NULL,(const uint64_t *) d_bucket,sh,d_query,NULL,nq,d_pos);
+      else
+        find_keys_kernel<uint32_t,1><<<(unsigned) nblk,128,0,st>>>(d_keys,NULL,(const uint32_t *) d_bucket,sh,d_query,NULL,nq,d_pos);
+    }
   else
-    find_keys_kernel<uint32_t><<<(unsigned) nblk,128,0,(cudaStream_t) stream>>>
-        (d_keys,(const uint32_t *) d_bucket,64-bits,d_query,nq,d_pos);
+    { if (idx64)
+        find_keys_kernel<uint64_t,2><<<(unsigned) nblk,128,0,st>>>(d_keys,d_keys_lo,(const uint64_t *) d_bucket,sh,d_query,d_query_lo,nq,d_pos);
+      else
+        find_keys_kernel<uint32_t,2><<<(unsigned) nblk,128,0,st>>>(d_keys,d_keys_lo,(const uint32_t *) d_bucket,sh,d_query,d_query_lo,nq,d_pos);
+    }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return hm_cuda_fail(e,"find_keys_kernel");

@@ -34,6 +34,7 @@ typedef struct
   { int                 dev;
     cudaStream_t        st, st_copy;
     uint64_t           *keys;
+    uint64_t           *keys_lo;      /* second key word, k > 32 only */
     uint16_t           *cnt;
     uint8_t            *deg;          /* n rounded up to 4 */
     void               *bucket;
@@ -66,6 +67,7 @@ int hm_peer_sum_plot(unsigned long long **plot, const int *dev, cudaStream_t *st
 static void free_dev(DevTable *D)
 { cudaSetDevice(D->dev);
   if (D->keys)   cudaFree(D->keys);
+  if (D->keys_lo) cudaFree(D->keys_lo);
   if (D->cnt)    cudaFree(D->cnt);
   if (D->deg)    cudaFree(D->deg);
   if (D->bucket) cudaFree(D->bucket);
@@ -203,7 +205,8 @@ static int load_range(hm_scan *s, DevTable *D, const hm_host_table *t, const int
           if (e != cudaSuccess) { rc = hm_cuda_fail(e,"cudaMemcpyAsync(H2D records)"); break; }
           cudaEventRecord(copied[b],D->st_copy);
           cudaStreamWaitEvent(D->st,copied[b],0);
-          rc = hm_k_unpack_records(stage[b],m,o,d_index,t->ibyte,t->kmer,D->keys+o,D->cnt+o,D->st);
+          rc = hm_k_unpack_records(stage[b],m,o,d_index,t->ibyte,t->kmer,D->keys+o,
+                                   D->keys_lo ? D->keys_lo+o : NULL,D->cnt+o,D->st);
           s->launches += 1;
           cudaEventRecord(unpacked[b],D->st);
           used[b] = 1;
@@ -261,6 +264,8 @@ extern "C" int hm_scan_create(const hm_host_table *t, const int *dev, int n_gpus
       TRY(cudaStreamCreateWithFlags(&D->st,cudaStreamNonBlocking));
       TRY(cudaStreamCreateWithFlags(&D->st_copy,cudaStreamNonBlocking));
       TRY(cudaMalloc(&D->keys,sizeof(uint64_t)*(size_t) (n+1)));
+      if (t->kmer > 32)
+        TRY(cudaMalloc(&D->keys_lo,sizeof(uint64_t)*(size_t) (n+1)));
       TRY(cudaMalloc(&D->cnt,sizeof(uint16_t)*(size_t) (n+1)));
       TRY(cudaMalloc(&D->deg,(size_t) ((n+4)&~3ll)));
       TRY(cudaMalloc(&D->bucket,ib*(((size_t) 1<<s->bits)+1)));
@@ -295,6 +300,9 @@ extern "C" int hm_scan_create(const hm_host_table *t, const int *dev, int n_gpus
               cudaSetDevice(D->dev);
               cudaError_t e = cudaMemcpyPeerAsync(D->keys+S->lo,D->dev,S->keys+S->lo,S->dev,
                                                   sizeof(uint64_t)*(size_t) m,D->st);
+              if (e == cudaSuccess && D->keys_lo != NULL)
+                e = cudaMemcpyPeerAsync(D->keys_lo+S->lo,D->dev,S->keys_lo+S->lo,S->dev,
+                                        sizeof(uint64_t)*(size_t) m,D->st);
               if (e == cudaSuccess)
                 e = cudaMemcpyPeerAsync(D->cnt+S->lo,D->dev,S->cnt+S->lo,S->dev,
                                         sizeof(uint16_t)*(size_t) m,D->st);
@@ -337,6 +345,15 @@ static uint64_t revcomp64(uint64_t x, int k)
   return x;
 }
 
+/* reverse complement of a left-aligned packed k-mer of 33..64 bases held in two words */
+static void revcomp128(uint64_t hi, uint64_t lo, int k, uint64_t *rhi, uint64_t *rlo)
+{ /* reversing all 64 slots swaps the words; the k real bases end up right-aligned over 128 bits */
+  uint64_t a = revcomp64(lo,32), b = revcomp64(hi,32);      /* full-word reverse complements */
+  int      sh = 2*(64-k);                                    /* pad slots now sit on top: shift them out */
+  if (sh == 0) { *rhi = a; *rlo = b; }
+  else         { *rhi = (a << sh) | (b >> (64-sh)); *rlo = b << sh; }
+}
+
 /* examine_table (PloidyPlot.c:1167-1230).  trim: smallest non-zero count among the middle <=1e8
  * entries >= ethresh.  symm: reverse complement of entry 1 (moving on past palindromes, where
  * the reference's loop would never terminate) is present.                                      */
@@ -346,6 +363,7 @@ extern "C" int hm_scan_examine(hm_scan *s, int ethresh, int *trim, int *symm)
   int       h_min = 0x8000, *d_min = NULL;
   uint64_t *d_q = NULL;
   int64_t  *d_pos = NULL;
+  int       two = (D->keys_lo != NULL);
 
   HM_CUDA(cudaSetDevice(D->dev));
   if (n+3 < 100000000) { frst = 0; last = n; }
@@ -365,17 +383,20 @@ extern "C" int hm_scan_examine(hm_scan *s, int ethresh, int *trim, int *symm)
   *trim = (h_min >= ethresh);
 
   *symm = 1;
-  HM_CUDA(cudaMalloc(&d_q,sizeof(uint64_t)));
+  HM_CUDA(cudaMalloc(&d_q,2*sizeof(uint64_t)));
   HM_CUDA(cudaMalloc(&d_pos,sizeof(int64_t)));
   for (int64_t sidx = 1; sidx < n; sidx++)
-    { uint64_t x, q;
+    { uint64_t x, xw = 0, q[2];
       int64_t  pos;
       cudaError_t e = cudaMemcpyAsync(&x,D->keys+sidx,sizeof(uint64_t),cudaMemcpyDeviceToHost,D->st);
+      if (e == cudaSuccess && two)
+        e = cudaMemcpyAsync(&xw,D->keys_lo+sidx,sizeof(uint64_t),cudaMemcpyDeviceToHost,D->st);
       if (e == cudaSuccess) e = cudaStreamSynchronize(D->st);
       if (e != cudaSuccess) { rc = hm_cuda_fail(e,"examine: key fetch"); break; }
-      q = revcomp64(x,s->kmer);
-      cudaMemcpyAsync(d_q,&q,sizeof(uint64_t),cudaMemcpyHostToDevice,D->st);
-      rc = hm_k_find_keys(D->keys,n,D->bucket,s->bits,s->idx64,d_q,1,d_pos,D->st);
+      if (two) revcomp128(x,xw,s->kmer,q,q+1);
+      else     { q[0] = revcomp64(x,s->kmer); q[1] = 0; }
+      cudaMemcpyAsync(d_q,q,2*sizeof(uint64_t),cudaMemcpyHostToDevice,D->st);
+      rc = hm_k_find_keys(D->keys,D->keys_lo,n,D->bucket,s->bits,s->idx64,d_q,two ? d_q+1 : NULL,1,d_pos,D->st);
       s->launches += 1;
       if (rc != HM_OK) break;
       e = cudaMemcpyAsync(&pos,d_pos,sizeof(int64_t),cudaMemcpyDeviceToHost,D->st);
@@ -430,7 +451,7 @@ extern "C" int hm_scan_run(hm_scan *s, int64_t *plot, hm_scan_stats *stats)
   for (int g = 0; g < G; g++)
     { DevTable *D = s->d+g;
       HM_CUDA(cudaSetDevice(D->dev));
-      rc = hm_k_pass1_degree(D->keys,D->cnt,n,D->bucket,s->bits,s->idx64,D->filter,s->fpos,s->kmer,
+      rc = hm_k_pass1_degree(D->keys,D->keys_lo,D->cnt,n,D->bucket,s->bits,s->idx64,D->filter,s->fpos,s->kmer,
                              D->lo,D->hi,D->deg,D->up,peer_mode ? &sh[g] : NULL,D->st);
       if (rc != HM_OK) return rc;
       s->launches += (D->hi > D->lo);
@@ -513,12 +534,14 @@ extern "C" int hm_hetmers_host(const hm_host_table *t, const int *dev, int n_gpu
   return rc;
 }
 
-extern "C" int hm_scan_download(hm_scan *s, uint64_t *keys, uint16_t *cnt, uint8_t *deg)
+extern "C" int hm_scan_download(hm_scan *s, uint64_t *keys, uint64_t *keys_lo, uint16_t *cnt, uint8_t *deg)
 { DevTable *D = s->d;
   HM_CUDA(cudaSetDevice(D->dev));
   HM_CUDA(cudaStreamSynchronize(D->st));
   if (keys != NULL)
     HM_CUDA(cudaMemcpy(keys,D->keys,sizeof(uint64_t)*(size_t) s->n,cudaMemcpyDeviceToHost));
+  if (keys_lo != NULL && D->keys_lo != NULL)
+    HM_CUDA(cudaMemcpy(keys_lo,D->keys_lo,sizeof(uint64_t)*(size_t) s->n,cudaMemcpyDeviceToHost));
   if (cnt != NULL)
     HM_CUDA(cudaMemcpy(cnt,D->cnt,sizeof(uint16_t)*(size_t) s->n,cudaMemcpyDeviceToHost));
   if (deg != NULL)                      /* every owner's slice (identical copies in dense mode) */

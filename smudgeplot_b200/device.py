@@ -2,7 +2,8 @@
 only), every computation is one of our CUDA kernels in libhetmers_b200.so.
 
 `DeviceTable` holds the structure-of-arrays table of DESIGN.md §3 in torch tensors:
-    keys  int64[n]   (bit pattern of the left-aligned uint64 packed k-mer)
+    keys  int64[n]   (bit pattern of the left-aligned uint64 packed k-mer, bases 0..31)
+    keys_lo int64[n] (bases 32..63, k > 32 only)
     cnt   int16[n]   (bit pattern of the uint16 count)
     deg   uint8[n+]  (the reference's `Pair` incidence array, PloidyPlot.c:163)
     bucket int32/int64[(1<<bits)+1]
@@ -27,8 +28,10 @@ def _stream():
 
 class DeviceTable:
     def __init__(self, kmer: int, keys: torch.Tensor, cnt: torch.Tensor, bits: int | None = None,
-                 fbits: int | None = None):
+                 fbits: int | None = None, keys_lo: torch.Tensor | None = None):
         assert keys.is_cuda and keys.dtype == torch.int64 and keys.is_contiguous()
+        assert (kmer > 32) == (keys_lo is not None), "k > 32 needs the second key word (keys_lo)"
+        self.keys_lo = keys_lo
         assert cnt.is_cuda and cnt.dtype == torch.int16 and cnt.is_contiguous()
         self.L = _lib.lib()
         self.kmer = kmer
@@ -51,7 +54,7 @@ class DeviceTable:
     # ---- construction -------------------------------------------------------------------
     @classmethod
     def from_records(cls, kmer: int, ibyte: int, records: torch.Tensor, index: torch.Tensor,
-                     first: int = 0, n_total: int | None = None, out=None):
+                     first: int = 0, n_total: int | None = None, out=None, out_lo=None):
         """Unpack raw FastK part records (uint8[n*pbyte], on the device) holding table ordinals
         [first, first+n) into SoA tensors; `index` is the stub index int64[1<<8*ibyte] on the
         device.  With `out=(keys, cnt)` (full-table tensors) the shard is written in place."""
@@ -59,18 +62,23 @@ class DeviceTable:
         kbyte = (kmer + 3) >> 2
         pbyte = kbyte - ibyte + 2
         n = records.numel() // pbyte
+        lv = klo = None
         if out is None:
             keys = torch.empty(n, dtype=torch.int64, device=records.device)
             cnt = torch.empty(n, dtype=torch.int16, device=records.device)
             kv, cv = keys, cnt
+            if kmer > 32:
+                klo = lv = torch.empty(n, dtype=torch.int64, device=records.device)
         else:
             keys, cnt = out
             kv, cv = keys[first:first + n], cnt[first:first + n]
+            if kmer > 32:
+                lv = out_lo[first:first + n]
         with torch.cuda.device(records.device):
             _lib.check(L.hm_k_unpack_records(_ptr(records), n, first, _ptr(index), ibyte, kmer,
-                                             _ptr(kv), _ptr(cv), _stream()))
+                                             _ptr(kv), _ptr(lv), _ptr(cv), _stream()))
         if out is None:
-            t = cls(kmer, keys, cnt)
+            t = cls(kmer, keys, cnt, keys_lo=klo)
             t.launches += 1
             return t
         return None
@@ -105,7 +113,7 @@ class DeviceTable:
     def pass1(self):
         """neighbour search + degree (hm_k_pass1_degree) over [lo,hi); deg must be zero."""
         with torch.cuda.device(self.device):
-            _lib.check(self.L.hm_k_pass1_degree(_ptr(self.keys), _ptr(self.cnt), self.n, _ptr(self.bucket),
+            _lib.check(self.L.hm_k_pass1_degree(_ptr(self.keys), _ptr(self.keys_lo), _ptr(self.cnt), self.n, _ptr(self.bucket),
                                                 self.bits, self.idx64, _ptr(self.filter), self.fbits, self.kmer,
                                                 self.lo, self.hi,
                                                 self._deg(), _ptr(self.up), self._shards(), _stream()))
@@ -139,10 +147,11 @@ class DeviceTable:
         self.launches += 1
         return int(out.item())
 
-    def find(self, queries: torch.Tensor) -> torch.Tensor:
+    def find(self, queries: torch.Tensor, queries_lo: torch.Tensor | None = None) -> torch.Tensor:
         pos = torch.empty(queries.numel(), dtype=torch.int64, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self.L.hm_k_find_keys(_ptr(self.keys), self.n, _ptr(self.bucket), self.bits, self.idx64,
-                                             _ptr(queries), queries.numel(), _ptr(pos), _stream()))
+            _lib.check(self.L.hm_k_find_keys(_ptr(self.keys), _ptr(self.keys_lo), self.n, _ptr(self.bucket), self.bits,
+                                             self.idx64, _ptr(queries), _ptr(queries_lo), queries.numel(), _ptr(pos),
+                                             _stream()))
         self.launches += 1
         return pos

@@ -40,10 +40,12 @@ def shard_offsets(local_n: int, group=None, device=None):
     return sizes, offs[:-1], offs[-1]
 
 
-def gather_table(local_keys: torch.Tensor, local_cnt: torch.Tensor, group=None, out=None):
+def gather_table(local_keys: torch.Tensor, local_cnt: torch.Tensor, group=None, out=None,
+                 local_lo: torch.Tensor | None = None, out_lo: torch.Tensor | None = None):
     """Assemble the full sorted table on every rank from per-rank shards (shard r = rank r's
     slice of the key space, so concatenation in rank order is the sorted table).
-    -> (keys_full, cnt_full, lo, hi) with [lo,hi) this rank's index range."""
+    -> (keys_full, cnt_full, lo, hi) with [lo,hi) this rank's index range; with `local_lo` (second
+    key word, k > 32) -> (keys_full, cnt_full, lo, hi, keys_lo_full)."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     sizes, offs, total = shard_offsets(local_keys.numel(), group, local_keys.device)
     if out is None:
@@ -51,17 +53,26 @@ def gather_table(local_keys: torch.Tensor, local_cnt: torch.Tensor, group=None, 
         cnt = torch.empty(total, dtype=local_cnt.dtype, device=local_cnt.device)
     else:
         keys, cnt = out
+    klo = None
+    if local_lo is not None:
+        klo = out_lo if out_lo is not None else torch.empty(total, dtype=local_lo.dtype, device=local_lo.device)
     lo, hi = offs[rank], offs[rank] + sizes[rank]
     if local_keys.data_ptr() != keys[lo:hi].data_ptr():
         keys[lo:hi].copy_(local_keys)
         cnt[lo:hi].copy_(local_cnt)
+    if klo is not None and local_lo.data_ptr() != klo[lo:hi].data_ptr():
+        klo[lo:hi].copy_(local_lo)
     for r in range(world):
         if sizes[r] == 0:
             continue
         src = dist.get_global_rank(group, r) if group is not None else r
         dist.broadcast(keys[offs[r]:offs[r] + sizes[r]], src=src, group=group)
+        if klo is not None:
+            dist.broadcast(klo[offs[r]:offs[r] + sizes[r]], src=src, group=group)
         # counts travel as raw bytes (gloo has no int16 broadcast; NCCL does not care)
         dist.broadcast(cnt[offs[r]:offs[r] + sizes[r]].view(torch.uint8), src=src, group=group)
+    if klo is not None:
+        return keys, cnt, lo, hi, klo
     return keys, cnt, lo, hi
 
 
@@ -159,12 +170,12 @@ class PeerDeg:
 class ShardedScan:
     """device-resident replica + this rank's work range; `scan()` = T_scan of SURVEY.md §8d"""
 
-    def __init__(self, kmer, keys_full, cnt_full, lo, hi, group=None):
+    def __init__(self, kmer, keys_full, cnt_full, lo, hi, group=None, keys_lo_full=None):
         from .device import DeviceTable
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        self.table = DeviceTable(kmer, keys_full, cnt_full).build_index()
+        self.table = DeviceTable(kmer, keys_full, cnt_full, keys_lo=keys_lo_full).build_index()
         self.table.alloc_work(lo, hi)
         self.kmer, self.lo, self.hi = kmer, lo, hi
         self.n_total = keys_full.numel()
@@ -191,6 +202,10 @@ class ShardedScan:
         keys, cnt = synth.synth_table(k, G, ploidy, het, cov, L, seed, device=device, key_range=rng)
         cnt16 = cnt.to(torch.int16)
         del cnt
+        if k > 32:                               # two key words per k-mer
+            khi, klo = keys[:, 0].contiguous(), keys[:, 1].contiguous()
+            kf, cf, lo, hi, lf = gather_table(khi, cnt16, group, local_lo=klo)
+            return cls(k, kf, cf, lo, hi, group, keys_lo_full=lf)
         kf, cf, lo, hi = gather_table(keys, cnt16, group)
         del keys, cnt16
         return cls(k, kf, cf, lo, hi, group)

@@ -129,18 +129,23 @@ def unpack_host(kt: KtabFiles):
 
 
 def keys_u64_to_bytes(keys_u64: np.ndarray, kmer: int) -> np.ndarray:
-    """left-aligned uint64 packed k-mers (k<=32) -> uint8[n,kbyte] big-endian."""
+    """left-aligned packed k-mers -> uint8[n,kbyte] big-endian.  uint64[n] for k<=32, or
+    uint64[n,2] = (bases 0..31, bases 32..63) for 32 < k <= 64."""
     kb = (kmer + 3) >> 2
-    be = np.ascontiguousarray(keys_u64.astype(">u8")).view(np.uint8).reshape(-1, 8)
+    a = np.ascontiguousarray(np.asarray(keys_u64, dtype=np.uint64))
+    words = 1 if a.ndim == 1 else a.shape[1]
+    be = np.ascontiguousarray(a.reshape(-1, words).astype(">u8")).view(np.uint8).reshape(-1, 8 * words)
     return np.ascontiguousarray(be[:, :kb])
 
 
 def keys_bytes_to_u64(keys: np.ndarray) -> np.ndarray:
-    """uint8[n,kbyte<=8] big-endian -> left-aligned uint64."""
+    """uint8[n,kbyte] big-endian -> left-aligned uint64[n] (kbyte<=8) or uint64[n,2] (kbyte<=16)."""
     n, kb = keys.shape
-    buf = np.zeros((n, 8), dtype=np.uint8)
+    words = 1 if kb <= 8 else 2
+    buf = np.zeros((n, 8 * words), dtype=np.uint8)
     buf[:, :kb] = keys
-    return buf.view(">u8").reshape(n).astype(np.uint64)
+    out = buf.view(">u8").reshape(n, words).astype(np.uint64)
+    return out[:, 0] if words == 1 else out
 
 
 def write_ktab(name: str, kmer: int, keys: np.ndarray, cnt: np.ndarray, ibyte: int = 3,
@@ -149,8 +154,8 @@ def write_ktab(name: str, kmer: int, keys: np.ndarray, cnt: np.ndarray, ibyte: i
     (or left-aligned uint64[n] for k<=32); `cnt`: uint16[n].  Parts are cut on prefix-bucket
     boundaries unless cut_on_buckets=False (SURVEY.md Appendix A discusses why that matters to
     the reference's on-disk bisection)."""
-    if keys.ndim == 1:
-        keys = keys_u64_to_bytes(keys.astype(np.uint64), kmer)
+    if keys.dtype != np.uint8:
+        keys = keys_u64_to_bytes(keys, kmer)
     n, kb = keys.shape
     assert kb == (kmer + 3) >> 2
     hb = kb - ibyte

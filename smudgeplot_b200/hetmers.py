@@ -103,10 +103,13 @@ class Scan:
     def download(self, deg: bool = True):
         n = self.kt.nels
         keys = np.empty(n, dtype=np.uint64)
+        klo = np.empty(n, dtype=np.uint64) if self.kt.kmer > 32 else None
         cnt = np.empty(n, dtype=np.uint16)
         d = np.empty(n, dtype=np.uint8) if deg else None
-        _lib.check(self._L.hm_scan_download(self._h, keys.ctypes.data, cnt.ctypes.data,
-                                            d.ctypes.data if deg else None))
+        _lib.check(self._L.hm_scan_download(self._h, keys.ctypes.data, klo.ctypes.data if klo is not None else None,
+                                            cnt.ctypes.data, d.ctypes.data if deg else None))
+        if klo is not None:
+            keys = np.stack([keys, klo], axis=1)          # [n, 2] (hi, lo) words
         return keys, cnt, d
 
     def close(self):

@@ -32,6 +32,7 @@ CASES = {
     "tet_k32":   dict(k=32, G=2500,  ploidy=4, het=0.02, cov=80,  L=10, seed=5, ibyte=2, nparts=2, e=10),
     "dense_k11": dict(k=11, G=40000, ploidy=2, het=0.05, cov=30,  L=4,  seed=7, ibyte=1, nparts=3, e=4),
     "smax_k17":  dict(k=17, G=5000,  ploidy=2, het=0.03, cov=985, L=4,  seed=9, ibyte=1, nparts=1, e=4),
+    "dip_k40":   dict(k=40, G=3000,  ploidy=2, het=0.02, cov=40,  L=4,  seed=13, ibyte=1, nparts=2, e=4),
     "midcut_k21": dict(k=21, G=5000, ploidy=2, het=0.02, cov=40,  L=4,  seed=11, ibyte=1, nparts=4, e=4, midcut=True),
 }
 

@@ -101,6 +101,10 @@ CASES = [  # k, G, ploidy, het, cov, L, seed, ibyte, nparts
     (32, 40000, 2, 0.03, 40, 4, 103, 3, 1),
     (12, 200000, 2, 0.02, 30, 4, 104, 3, 2),      # kbyte == ibyte: records are counts only
     (4, 300, 2, 0.2, 30, 1, 105, 1, 1),           # tiny k, saturated neighbourhoods
+    (33, 60000, 2, 0.02, 40, 4, 106, 3, 2),       # two 64-bit words per k-mer from here on
+    (40, 80000, 3, 0.02, 60, 8, 107, 3, 3),       # FastK's default k
+    (47, 50000, 2, 0.03, 40, 4, 108, 2, 1),
+    (64, 40000, 4, 0.02, 80, 10, 109, 3, 2),
 ]
 
 
@@ -171,9 +175,50 @@ def test_result_independent_of_bucket_bits_and_work_split():
 
 # ------------------------------------------------------------------ (c) vs the reference binary
 
-@pytest.mark.parametrize("k,target,ploidy,het,cov,L,seed", [(21, 1_000_000, 2, 0.01, 40, 4, 1),      # BASELINE config 1
-                                                           (31, 20_000_000, 2, 0.01, 40, 12, 2)])   # config 2 at 1/10
-def test_medium_table_matches_reference_binary(k, target, ploidy, het, cov, L, seed, tmp_path):
+def test_long_kmer_work_split_and_filter_widths():
+    """k = 40 (two key words): plot independent of bucket / filter width and of the work split"""
+    import torch
+    from smudgeplot_b200.device import DeviceTable
+    keys, cnt = synth.synth_table(40, 50000, 3, 0.02, 60, 8, 55, device="cuda")
+    khi, klo, c16 = keys[:, 0].contiguous(), keys[:, 1].contiguous(), cnt.to(torch.int16)
+    ref = None
+    for bits, fbits in ((3, 22), (14, 27), (16, 32), (15, 35), (16, 37)):
+        t = DeviceTable(40, khi, c16, bits=bits, fbits=fbits, keys_lo=klo).build_index()
+        p = t.scan().clone()
+        ref = p if ref is None else ref
+        assert torch.equal(p, ref), (bits, fbits)
+    n = khi.numel()
+    deg = torch.zeros((n + 4) & ~3, dtype=torch.uint8, device="cuda")
+    plot = torch.zeros_like(ref).view(-1)
+    parts = []
+    for lo, hi in ((0, n // 3), (n // 3, n - 5), (n - 5, n)):
+        w = DeviceTable(40, khi, c16, keys_lo=klo)
+        w.bucket, w.filter = t.bucket, t.filter
+        w.bits, w.fbits = t.bits, t.fbits
+        w.alloc_work(lo, hi)
+        w.deg = deg
+        w.pass1()
+        parts.append(w)
+    for w in parts:
+        w.plot = plot
+        w.pass2()
+    torch.cuda.synchronize()
+    assert torch.equal(plot.view_as(ref), ref)
+    rhi, rlo = synth.revcomp_long(khi, klo, 40)
+    pos = t.find(rhi, rlo)
+    assert bool((pos >= 0).all())                       # symmetric table: every reverse complement is found
+
+
+@pytest.mark.parametrize("k,target,ploidy,het,cov,L,seed,ref_threads", [
+    (21, 1_000_000, 2, 0.01, 40, 4, 1, 1),        # BASELINE configs[0]: reference C hetmers on 1 CPU thread
+    (31, 20_000_000, 2, 0.01, 40, 12, 2, 0),      # configs[1] at 1/10 of the bench size
+    (31, 30_000_000, 4, 0.01, 40, 12, 3, 0),      # stand-in for configs[2] (the real S. cerevisiae table needs
+                                                  #   network + FastK): synthetic tetraploid ~3e7, clearly not real data
+    (31, 12_000_000, 3, 0.01, 60, 12, 4, 0),      # configs[3] parameters (triploid cov 60) at reduced size
+    (31, 12_000_000, 4, 0.02, 80, 10, 5, 0),      # configs[4] parameters (tetraploid het 2% cov 80, L=10), reduced
+    (40, 5_000_000, 2, 0.01, 40, 4, 6, 0),        # FastK's default k=40: two-word keys against the reference
+])
+def test_medium_table_matches_reference_binary(k, target, ploidy, het, cov, L, seed, ref_threads, tmp_path):
     G = synth.calibrate_G(k, target, ploidy, het, cov, L)
     keys, cnt = synth.synth_table(k, G, ploidy, het, cov, L, seed, device="cuda")
     name = str(tmp_path / "t")
@@ -183,7 +228,7 @@ def test_medium_table_matches_reference_binary(k, target, ploidy, het, cov, L, s
     hetmers.run_hetmers(name, o=out, L=L, t=4)
     got = open(out + ".smu").read()
     if ou.have_ref():
-        r = ou.run_ref(name, str(tmp_path / "ref"), L, threads=min(os.cpu_count() or 4, 64))
+        r = ou.run_ref(name, str(tmp_path / "ref"), L, threads=ref_threads or min(os.cpu_count() or 4, 64))
         assert r.returncode == 0, r.stderr
         want = open(str(tmp_path / "ref.smu")).read()
     else:

@@ -105,7 +105,9 @@ def synth_table(k: int, G: int, ploidy: int = 2, het: float = 0.01, cov: float =
     extra_hom_repeats: append that many tandem copies of the first 10k bases to every haplotype
     (gives entries with occurrences > ploidy, i.e. >2 neighbours per position in rare cases).
     """
-    assert 1 <= k <= 32 and G >= k
+    assert 1 <= k <= 64 and G >= k
+    if k > 32:
+        return _synth_table_long(k, G, ploidy, het, cov, L, seed, device, key_range, extra_hom_repeats)
     dev = torch.device(device)
     base0 = _hash_idx(G, seed * 1000003 + 1, dev) & 3
     if extra_hom_repeats:
@@ -153,6 +155,76 @@ def synth_table(k: int, G: int, ploidy: int = 2, het: float = 0.01, cov: float =
     cnt = torch.clamp(cnt, max=32767)
     keep = cnt >= L
     return keys[keep].contiguous(), cnt[keep].to(torch.int32).contiguous()
+
+
+def revcomp_long(hi: torch.Tensor, lo: torch.Tensor, k: int):
+    """reverse complement of left-aligned packed k-mers with 32 < k <= 64 held as (hi, lo) words"""
+    a, b = reverse2(~lo), reverse2(~hi)          # all 64 slots reversed: the words swap
+    sh = 2 * (64 - k)                            # complemented pad now on top: shift it out
+    if sh == 0:
+        return a, b
+    return (a << sh) | _lsr(b, 64 - sh), b << sh
+
+
+def _haplotype_bases(G, ploidy, het, seed, dev, extra_hom_repeats):
+    base0 = _hash_idx(G, seed * 1000003 + 1, dev) & 3
+    if extra_hom_repeats:
+        rep = base0[: min(10000, G)]
+        base0 = torch.cat([base0] + [rep] * extra_hom_repeats)
+        G = base0.numel()
+    het_thr = int(het * float(1 << 53))
+    haps = [base0]
+    for h in range(1, ploidy):
+        hsh = _hash_idx(G, seed * 1000003 + 17 * h + 5, dev)
+        is_snp = _lsr(hsh, 11) < het_thr
+        delta = 1 + (hsh & 0x7FF) % 3
+        haps.append(torch.where(is_snp, (base0 + delta) & 3, base0))
+    return haps, G
+
+
+def _synth_table_long(k, G, ploidy, het, cov, L, seed, device, key_range, extra_hom_repeats):
+    """k in 33..64: same model, keys returned as int64[n,2] = (bases 0..31, bases 32..k-1) words"""
+    dev = torch.device(device)
+    haps, G = _haplotype_bases(G, ploidy, het, seed, dev, extra_hom_repeats)
+    n_k = G - k + 1
+    his, los = [], []
+    for b in haps:
+        hi = torch.zeros(n_k, dtype=torch.int64, device=dev)
+        lo = torch.zeros(n_k, dtype=torch.int64, device=dev)
+        for j in range(32):
+            hi = (hi << 2) | b[j:j + n_k]
+        for j in range(32, k):
+            lo = (lo << 2) | b[j:j + n_k]
+        lo = lo << (2 * (64 - k))
+        rhi, rlo = revcomp_long(hi, lo, k)
+        his += [hi, rhi]
+        los += [lo, rlo]
+    hi, lo = torch.cat(his), torch.cat(los)
+    del his, los
+    if key_range is not None:
+        pre = _lsr(hi, 40)
+        m = (pre >= key_range[0]) & (pre < key_range[1])
+        hi, lo = hi[m], lo[m]
+    pairs = torch.stack([hi ^ _SIGN, lo ^ _SIGN], dim=1)
+    del hi, lo
+    uniq, occ = torch.unique(pairs, dim=0, sorted=True, return_counts=True)
+    del pairs
+    hi, lo = uniq[:, 0] ^ _SIGN, uniq[:, 1] ^ _SIGN
+    rhi, rlo = revcomp_long(hi, lo, k)
+    fwd_smaller = ((hi ^ _SIGN) < (rhi ^ _SIGN)) | ((hi == rhi) & ((lo ^ _SIGN) < (rlo ^ _SIGN)))
+    chi, clo = torch.where(fwd_smaller, hi, rhi), torch.where(fwd_smaller, lo, rlo)
+    u = _lsr(mix64(mix64(chi ^ _s64(mix_int(seed * 7919 + 3))) ^ clo), 11)
+    lam1 = cov / ploidy
+    mmax = 64
+    cmax = int(lam1 * mmax + 12 * math.sqrt(lam1 * mmax) + 16)
+    flat = torch.from_numpy(_poisson_tables(lam1, mmax, cmax)).to(dev)
+    m = torch.clamp(occ, max=mmax)
+    cnt = torch.clamp(torch.searchsorted(flat, (m << 53) | u, right=True) - m * cmax, max=cmax - 1)
+    cnt = torch.where(occ > mmax, (occ.double() * lam1).round().long(), cnt)
+    cnt = torch.clamp(cnt, max=32767)
+    keep = cnt >= L
+    keys = torch.stack([hi[keep], lo[keep]], dim=1).contiguous()
+    return keys, cnt[keep].to(torch.int32).contiguous()
 
 
 def keys_to_u64_numpy(keys: torch.Tensor) -> np.ndarray:
