@@ -67,7 +67,7 @@ def main():
         assert outs[0] == outs[1], f"{name}: reference output depends on -T ?"
         os.rename(os.path.join(d, "ref_T1.smu"), os.path.join(d, name + ".smu"))
         os.remove(os.path.join(d, "ref_T4.smu"))
-        meta[name] = dict(c, nels=int(keys.numel()), smu_rows=len(outs[0].splitlines()),
+        meta[name] = dict(c, nels=int(keys.shape[0]), smu_rows=len(outs[0].splitlines()),
                           verbose=[ln.strip() for ln in r.stderr.splitlines() if "input table" in ln])
         print(name, meta[name]["nels"], "entries,", meta[name]["smu_rows"], "rows")
 
