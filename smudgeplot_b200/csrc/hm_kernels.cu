@@ -63,7 +63,7 @@ extern "C" int hm_pick_bucket_bits(int64_t n)
   while (lg < 62 && ((int64_t) 1 << (lg+1)) <= n)
     lg += 1;                                  /* floor(log2 n) */
   int bits = lg-1;                            /* ~2-4 entries per bucket */
-  if (bits > 28) bits = 28;
+  if (bits > 30) bits = 30;
   if (bits < 2)  bits = 2;
   return bits;
 }
