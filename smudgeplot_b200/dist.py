@@ -109,7 +109,7 @@ def balanced_offsets(keys_full: torch.Tensor, world: int):
     marks = torch.tensor([(b << 62) ^ sign if b < 2 else ((b << 62) - (1 << 64)) ^ sign for b in (1, 2, 3)],
                          dtype=torch.int64, device=keys_full.device)
     bnd = [0] + [int(v) for v in torch.searchsorted(flipped, marks).tolist()] + [n]
-    w = [1.0 + 0.045 * (3 - b) for b in range(4)]                # relative cost per entry by first base
+    w = [1.0 + 0.03 * (3 - b) for b in range(4)]                 # relative cost per entry by first base
     total = sum(w[b] * (bnd[b + 1] - bnd[b]) for b in range(4))
     offs, acc, b, pos = [0], 0.0, 0, 0
     for r in range(1, world):
