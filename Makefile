@@ -14,7 +14,8 @@ OBJDIR := build
 LIB    := $(LIBDIR)/libhetmers_b200.so
 BIN    := $(BINDIR)/hetmers
 
-CU_SRC := smudgeplot_b200/csrc/hm_kernels.cu smudgeplot_b200/csrc/hm_scan.cu smudgeplot_b200/csrc/hm_peer.cu
+CU_SRC := smudgeplot_b200/csrc/hm_kernels.cu smudgeplot_b200/csrc/hm_scan.cu smudgeplot_b200/csrc/hm_peer.cu \
+          smudgeplot_b200/csrc/hm_condition.cu
 CU_OBJ := $(patsubst smudgeplot_b200/csrc/%.cu,$(OBJDIR)/%.o,$(CU_SRC))
 C_OBJ  := $(OBJDIR)/fastk_table.o
 HDRS   := include/hetmers_b200.h smudgeplot_b200/csrc/hm_internal.h

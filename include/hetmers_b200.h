@@ -193,6 +193,11 @@ void hm_set_io_threads(int n);
 void hm_scan_destroy(hm_scan *s);
 /* examine_table decisions (PloidyPlot.c:1167-1230) computed on the device */
 int  hm_scan_examine(hm_scan *s, int ethresh, int *trim, int *symm);
+/* Condition the device-resident table in place: trim = drop entries with count < ethresh (what
+ * `Logex '...=A[<L>-]'` does), symm = add the reverse complement of every k-mer with the same
+ * count (what `Symmex` does) -- PloidyPlot.c:1381-1426 shells out to those FastK tools; here the
+ * table never leaves the GPU.  *nels_out = entries afterwards.                                  */
+int  hm_scan_condition(hm_scan *s, int ethresh, int do_trim, int do_symm, int64_t *nels_out);
 /* both passes; plot: host int64[HM_PLOT_CELLS]; stats optional */
 int  hm_scan_run(hm_scan *s, int64_t *plot, hm_scan_stats *stats);
 /* one call: create + run + destroy (what bench.py's e2e leg times) */

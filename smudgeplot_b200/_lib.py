@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "hm_k_min_count", "hm_k_find_keys", "hm_pick_bucket_bits",
     "hm_k_build_filter", "hm_filter_words", "hm_pick_filter_bits",
     "hm_dev_alloc", "hm_dev_free", "hm_ipc_export", "hm_ipc_open", "hm_ipc_close", "hm_p2p_native_atomics",
-    "hm_scan_create", "hm_set_io_threads", "hm_scan_destroy", "hm_scan_examine", "hm_scan_run", "hm_hetmers_host",
+    "hm_scan_create", "hm_set_io_threads", "hm_scan_destroy", "hm_scan_examine", "hm_scan_condition", "hm_scan_run", "hm_hetmers_host",
     "hm_scan_download", "hm_table_open", "hm_table_close", "hm_table_view", "hm_write_smu",
 ]
 
@@ -95,6 +95,7 @@ def lib():
     L.hm_scan_destroy.argtypes = [vp]
     L.hm_scan_destroy.restype = None
     L.hm_scan_examine.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
+    L.hm_scan_condition.argtypes = [vp, i32, i32, i32, C.POINTER(i64)]
     L.hm_scan_run.argtypes = [vp, vp, C.POINTER(ScanStats)]
     L.hm_hetmers_host.argtypes = [C.POINTER(HostTable), C.POINTER(i32), i32, vp, C.POINTER(ScanStats)]
     L.hm_scan_download.argtypes = [vp, vp, vp, vp, vp]

@@ -63,6 +63,9 @@ int hm_peer_enable(const int *dev, int n);
 int hm_peer_sum_deg(uint8_t **deg, const int64_t *lo, const int64_t *hi, const int *dev,
                     cudaStream_t *st, int n, int64_t nels);
 int hm_peer_sum_plot(unsigned long long **plot, const int *dev, cudaStream_t *st, int n);
+/* GPU trim / symmetrise (hm_condition.cu) */
+int hm_condition_arrays(int kmer, int ethresh, int do_trim, int do_symm,
+                        uint64_t **pk, uint64_t **pl, uint16_t **pc, int64_t *pn, cudaStream_t st);
 
 static void free_dev(DevTable *D)
 { cudaSetDevice(D->dev);
@@ -330,6 +333,67 @@ extern "C" int hm_scan_create(const hm_host_table *t, const int *dev, int n_gpus
   s->ms_alloc = t_alloc-t0; s->ms_records = t_rec-t_alloc; s->ms_index = now_ms()-t_rec;
   *out = s;
   return HM_OK;
+}
+
+/* Trim (count >= ethresh) and / or symmetrise (add reverse complements) the device-resident table
+ * in place: what the reference gets from `Logex` and `Symmex` (PloidyPlot.c:1381-1426), without
+ * leaving the GPU.  Every device conditions its own replica (deterministic, identical results);
+ * the index structures and work buffers are rebuilt for the new size.                          */
+extern "C" int hm_scan_condition(hm_scan *s, int ethresh, int do_trim, int do_symm, int64_t *nels_out)
+{ int     G = s->ngpu, rc = HM_OK;
+  int64_t n_new = -1;
+  if (!do_trim && !do_symm)
+    { if (nels_out) *nels_out = s->n;
+      return HM_OK;
+    }
+  for (int g = 0; g < G && rc == HM_OK; g++)
+    { DevTable *D = s->d+g;
+      int64_t   n = s->n;
+      HM_CUDA(cudaSetDevice(D->dev));
+      HM_CUDA(cudaStreamSynchronize(D->st));
+      if (D->deg)    { cudaFree(D->deg);    D->deg = NULL; }
+      if (D->up)     { cudaFree(D->up);     D->up = NULL; }
+      if (D->bucket) { cudaFree(D->bucket); D->bucket = NULL; }
+      if (D->filter) { cudaFree(D->filter); D->filter = NULL; }
+      rc = hm_condition_arrays(s->kmer,ethresh,do_trim,do_symm,&D->keys,&D->keys_lo,&D->cnt,&n,D->st);
+      s->launches += 6;
+      if (rc != HM_OK) return rc;
+      if (n_new >= 0 && n != n_new)
+        return hm_set_error(HM_ECUDA,"conditioning gave %lld entries on GPU %d but %lld on GPU 0",
+                            (long long) n,D->dev,(long long) n_new);
+      n_new = n;
+    }
+  s->n     = n_new;
+  s->bits  = hm_pick_bucket_bits(s->n);
+  s->fpos  = hm_pick_filter_bits(s->n);
+  s->idx64 = (s->n >= 0xFFFFFFF0ll);
+  size_t ib = s->idx64 ? 8 : 4;
+  for (int g = 0; g < G && rc == HM_OK; g++)
+    { DevTable *D = s->d+g;
+      int64_t   n = s->n;
+      cudaError_t e;
+      D->lo = n*g/G;
+      D->hi = n*(g+1)/G;
+#define TRY(call) if (rc == HM_OK && (e = (call)) != cudaSuccess) rc = hm_cuda_fail(e,#call)
+      TRY(cudaSetDevice(D->dev));
+      TRY(cudaMalloc(&D->deg,(size_t) ((n+4)&~3ll)));
+      TRY(cudaMalloc(&D->bucket,ib*(((size_t) 1<<s->bits)+1)));
+      TRY(cudaMalloc(&D->filter,sizeof(uint32_t)*(size_t) hm_filter_words(s->fpos)));
+      TRY(cudaMalloc(&D->up,ib*(size_t) (D->hi-D->lo+1)));
+#undef TRY
+      if (rc == HM_OK)
+        rc = hm_k_build_bucket_index(D->keys,n,s->bits,D->bucket,s->idx64,D->st);
+      if (rc == HM_OK)
+        rc = hm_k_build_filter(D->keys,n,s->fpos,D->filter,D->st);
+      s->launches += 2;
+    }
+  for (int g = 0; g < G; g++)
+    { cudaSetDevice(s->d[g].dev);
+      cudaError_t e = cudaStreamSynchronize(s->d[g].st);
+      if (rc == HM_OK && e != cudaSuccess) rc = hm_cuda_fail(e,"re-index after conditioning");
+    }
+  if (nels_out) *nels_out = s->n;
+  return rc;
 }
 
 /* reverse complement of a left-aligned packed k-mer (k <= 32) */

@@ -93,6 +93,14 @@ class Scan:
         _lib.check(self._L.hm_scan_examine(self._h, ethresh, C.byref(trim), C.byref(symm)))
         return bool(trim.value), bool(symm.value)
 
+    def condition(self, ethresh: int, trim: bool, symm: bool) -> int:
+        """trim (count >= ethresh) and / or symmetrise the device table in place (what the reference
+        gets from FastK's Logex / Symmex, PloidyPlot.c:1381-1426); returns the new entry count"""
+        n = C.c_int64()
+        _lib.check(self._L.hm_scan_condition(self._h, ethresh, int(trim), int(symm), C.byref(n)))
+        self.nels = n.value
+        return n.value
+
     def run(self):
         """-> (plot int64[1001,501], stats dict)"""
         plot = np.zeros(_lib.PLOT_CELLS, dtype=np.int64)
@@ -101,7 +109,7 @@ class Scan:
         return plot.reshape(_lib.SMAX + 1, _lib.PLOT_W), st.as_dict()
 
     def download(self, deg: bool = True):
-        n = self.kt.nels
+        n = getattr(self, "nels", self.kt.nels)
         keys = np.empty(n, dtype=np.uint64)
         klo = np.empty(n, dtype=np.uint64) if self.kt.kmer > 32 else None
         cnt = np.empty(n, dtype=np.uint16)
@@ -156,9 +164,8 @@ def write_smu(path: str, plot: np.ndarray) -> None:
 
 
 def hetmers(infile, o="smudgeplot", L=None, t=4, verbose=False, tmp=".", gpus: int = 1):
-    """In-process equivalent of the `hetmers` task for an already conditioned table: returns the
-    path of the .smu.  Tables that need trimming / symmetrising are handled by the executable
-    (run_hetmers), which shells out to FastK's tools exactly like the reference."""
+    """In-process equivalent of the `hetmers` task: returns the path of the .smu.  Tables that need
+    trimming / symmetrising are conditioned on the GPU (hm_scan_condition)."""
     if L is None:
         raise ValueError("-L (count threshold) is required")
     kt = read_ktab(infile, mmap=True)
@@ -169,7 +176,7 @@ def hetmers(infile, o="smudgeplot", L=None, t=4, verbose=False, tmp=".", gpus: i
                 ("trimmed and symmetric" if symm else "trimmed but not symmetric") if trim else
                 ("untrimmed yet symmetric" if symm else "untrimmed and not symmetric")))
         if not (trim and symm):
-            raise RuntimeError("table needs conditioning (trim=%d symm=%d): use run_hetmers()" % (trim, symm))
+            sc.condition(int(L), not trim, not symm)          # on the GPU (the reference: Logex / Symmex)
         plot, _ = sc.run()
     write_smu(f"{o}.smu", plot)
     return f"{o}.smu"

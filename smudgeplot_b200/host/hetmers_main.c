@@ -7,7 +7,8 @@
  *
  * mirrors main() of /root/reference/src/lib/PloidyPlot.c:1232-1630: argv grammar and messages
  * (gene_core.h:32-56 ARG_* macros), default output root, the "Found het-table" prompt, the
- * trimmed/symmetric examination and its shell-outs to FastK's Logex/Symmex/Fastrm, the verbose
+ * trimmed/symmetric examination (un-conditioned tables are trimmed / symmetrised on the GPU;
+ * HETMERS_EXTERNAL_CONDITIONING=1 restores the reference's shell-outs to FastK's Logex/Symmex/Fastrm), the verbose
  * lines, the .smu format and the exit codes.  -T is accepted (and clamped to 64 with the same
  * warning) but the GPU count comes from HETMERS_GPUS (default 1; "all" = every visible GPU).
  * There is no CPU fallback: without a CUDA device the program fails with exit 1.
@@ -239,6 +240,28 @@ int main(int argc, char *argv[])
 
     sprintf(tname,"%s",SRC);
 
+    if ((!trim || !symm) && getenv("HETMERS_EXTERNAL_CONDITIONING") == NULL)
+      { //  Condition the table where it already is -- on the GPU -- instead of shelling out to
+        //  FastK's Logex / Symmex and re-reading their output (same progress lines with -v)
+        int64_t nn;
+        if (VERBOSE)
+          { if (!trim)
+              fprintf(stderr,"\n  Trimming k-mers in table with count < %d\n",ETHRESH);
+            if (!symm)
+              fprintf(stderr,trim ? "\n  Making table symmetric\n" : "\n  Making trimmed table symmetric\n");
+            fflush(stderr);
+          }
+        if (hm_scan_condition(S,ETHRESH,!trim,!symm,&nn) != HM_OK)
+          die_hm();
+        if (nn < 2)
+          { fprintf(stderr,"%s: fewer than 2 k-mers are left after conditioning\n",Prog_Name);
+            exit (1);
+          }
+        free(command);
+        free(tname);
+      }
+    else
+      {
     if (!trim)
       { if (VERBOSE)
           { fprintf(stderr,"\n  Trimming k-mers in table with count < %d\n",ETHRESH);
@@ -280,6 +303,7 @@ int main(int argc, char *argv[])
       }
     else
       free(tname);
+      }
   }
 
   if (VERBOSE)

@@ -81,14 +81,109 @@ def test_examine_table_decisions(name, verdict, tool, golden_meta, tmp_path):
     table = os.path.join(GOLDEN, "conditioning", name)
     with hetmers.Scan(fastk.read_ktab(table)) as sc:
         assert sc.examine(c["e"]) == verdict
-    # the executable prints the reference's verdict and then shells out to the same FastK tool
+    # with HETMERS_EXTERNAL_CONDITIONING the executable prints the reference's verdict and then
+    # shells out to the same FastK tool with the same command line as the reference
+    env = dict(os.environ, HETMERS_EXTERNAL_CONDITIONING="1")
     r = subprocess.run([_lib.BIN_PATH, "-v", f"-e{c['e']}", "-T4", f"-o{tmp_path}/o", table],
-                       input="n\n", capture_output=True, text=True, cwd=tmp_path)
+                       input="n\n", capture_output=True, text=True, cwd=tmp_path, env=env)
     assert r.returncode == 1
     assert c["verbose"][0] in r.stderr
     if shutil.which(tool) is None:
         want = c["stderr_tail"][0].replace("/root/repo/tests/golden", GOLDEN)
         assert want in r.stderr                                         # "hetmers: Command '...' failed"
+
+
+def _condition_numpy(ku, cn, k, L, trim, symm):
+    """test-side restatement of Logex 'A[L-]' + Symmex (documented effect): keep count >= L, add
+    the reverse complement of every k-mer with the same count, originals win on duplicates."""
+    import torch
+    two = ku.ndim == 2
+    if trim:
+        keep = cn >= L
+        ku, cn = ku[keep], cn[keep]
+    if symm:
+        t = torch.from_numpy(ku.view(np.int64))
+        if two:
+            rh, rl = synth.revcomp_long(t[:, 0].contiguous(), t[:, 1].contiguous(), k)
+            rc = torch.stack([rh, rl], dim=1).numpy().view(np.uint64)
+        else:
+            rc = synth.revcomp_left(t, k).numpy().view(np.uint64)
+        allk = np.concatenate([ku, rc])
+        allc = np.concatenate([cn, cn])
+        kb = fastk.keys_u64_to_bytes(allk, k)
+        order = np.lexsort(tuple(kb[:, j] for j in range(kb.shape[1] - 1, -1, -1)))   # stable
+        kb, allc, allk = kb[order], allc[order], allk[order]
+        first = np.ones(len(kb), dtype=bool)
+        first[1:] = (kb[1:] != kb[:-1]).any(axis=1)
+        ku, cn = allk[first], allc[first]
+    return ku, cn
+
+
+@pytest.mark.parametrize("k,G,ploidy,seed,L", [(21, 60000, 2, 31, 6), (31, 80000, 3, 32, 12), (32, 50000, 2, 33, 5),
+                                               (40, 50000, 2, 34, 6), (12, 30000, 2, 35, 4)])
+def test_gpu_conditioning_of_canonical_untrimmed_table(k, G, ploidy, seed, L, tmp_path):
+    """a FastK-style table (canonical k-mers only, every count >= 1) is trimmed and symmetrised on
+    the GPU; the .smu must equal what the REFERENCE binary writes for the table conditioned by the
+    numpy restatement, and the -v lines must be the reference's"""
+    keys, cnt = synth.synth_table(k, G, ploidy, 0.02, 40, 1, seed)          # untrimmed: counts from 1
+    ku = synth.keys_to_u64_numpy(keys)
+    cn = cnt.numpy().astype(np.uint16)
+    import torch
+    if k > 32:
+        rh, rl = synth.revcomp_long(keys[:, 0].contiguous(), keys[:, 1].contiguous(), k)
+        rcb = fastk.keys_u64_to_bytes(torch.stack([rh, rl], 1).numpy().view(np.uint64), k)
+    else:
+        rcb = fastk.keys_u64_to_bytes(synth.revcomp_left(keys, k).numpy().view(np.uint64), k)
+    kb = fastk.keys_u64_to_bytes(ku, k)
+    w = kb.shape[1]
+    canon = kb.view(f"S{w}").reshape(-1) <= rcb.view(f"S{w}").reshape(-1)   # x <= rc(x)
+    raw = str(tmp_path / "raw")
+    fastk.write_ktab(raw, k, ku[canon], cn[canon], ibyte=3, nparts=3)
+    out = str(tmp_path / "gpu")
+    r = subprocess.run([_lib.BIN_PATH, "-v", f"-e{L}", "-T4", f"-o{out}", raw], input="n\n",
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stderr == ("\n  The input table is untrimmed and not symmetric\n"
+                        f"\n  Trimming k-mers in table with count < {L}\n"
+                        "\n  Making trimmed table symmetric\n"
+                        "\n  Starting to count covariant pairs\n"
+                        "\n  Count complete, outputting table\n")
+    ck, cc = _condition_numpy(ku[canon], cn[canon], k, L, True, True)
+    cond = str(tmp_path / "cond")
+    fastk.write_ktab(cond, k, ck, cc, ibyte=3, nparts=2)
+    if ou.have_ref():
+        rr = ou.run_ref(cond, str(tmp_path / "ref"), L, threads=4, verbose=True)
+        assert rr.returncode == 0 and "trimmed and symmetric" in rr.stderr, rr.stderr
+        want = open(str(tmp_path / "ref.smu")).read()
+    else:
+        rc, trim, symm, _ = ou.oracle_file(cond, L, str(tmp_path / "ora.smu"))
+        assert (rc, trim, symm) == (0, 1, 1)
+        want = open(str(tmp_path / "ora.smu")).read()
+    assert open(out + ".smu").read() == want and len(want) > 0
+    # in-process route + the conditioned table itself
+    with hetmers.Scan(fastk.read_ktab(raw)) as sc:
+        assert sc.examine(L) == (False, False)
+        n2 = sc.condition(L, True, True)
+        assert n2 == len(cc)
+        assert sc.examine(L) == (True, True)
+        k2, c2, _ = sc.download(deg=False)
+        plot, _ = sc.run()
+    assert np.array_equal(k2, ck) and np.array_equal(c2, cc)
+    assert hetmers.smu_text(plot) == want
+
+
+def test_gpu_conditioning_trim_only_and_symm_only(golden_meta, tmp_path):
+    # golden "untrimmed" (symmetric, -e9 above its smallest count) and "asymmetric" (one rc missing)
+    for name, (trim, symm) in (("untrimmed", (True, False)), ("asymmetric", (False, True))):
+        c = golden_meta["_conditioning"][name]
+        kt = fastk.read_ktab(os.path.join(GOLDEN, "conditioning", name))
+        kb, cn = fastk.unpack_host(kt)
+        ck, cc = _condition_numpy(fastk.keys_bytes_to_u64(kb), cn, 21, c["e"], trim, symm)
+        want_plot, _ = ou.oracle_scan(fastk.keys_u64_to_bytes(ck, 21), cc, 21)
+        with hetmers.Scan(kt) as sc:
+            assert sc.condition(c["e"], trim, symm) == len(cc)
+            plot, _ = sc.run()
+        assert np.array_equal(plot, want_plot)
 
 
 # ------------------------------------------------------------------ (b) seeded tables vs oracle
