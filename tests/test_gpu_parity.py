@@ -120,7 +120,7 @@ def _condition_numpy(ku, cn, k, L, trim, symm):
 
 
 @pytest.mark.parametrize("k,G,ploidy,seed,L", [(21, 60000, 2, 31, 6), (31, 80000, 3, 32, 12), (32, 50000, 2, 33, 5),
-                                               (40, 50000, 2, 34, 6), (12, 30000, 2, 35, 4)])
+                                               (40, 50000, 2, 34, 6), (12, 30000, 2, 35, 12)])
 def test_gpu_conditioning_of_canonical_untrimmed_table(k, G, ploidy, seed, L, tmp_path):
     """a FastK-style table (canonical k-mers only, every count >= 1) is trimmed and symmetrised on
     the GPU; the .smu must equal what the REFERENCE binary writes for the table conditioned by the
