@@ -28,7 +28,7 @@ def _stream():
 
 class DeviceTable:
     def __init__(self, kmer: int, keys: torch.Tensor, cnt: torch.Tensor, bits: int | None = None,
-                 fbits: int | None = None, keys_lo: torch.Tensor | None = None):
+                 fbits: int | None = None, keys_lo: torch.Tensor | None = None, force_idx64: bool = False):
         assert keys.is_cuda and keys.dtype == torch.int64 and keys.is_contiguous()
         assert (kmer > 32) == (keys_lo is not None), "k > 32 needs the second key word (keys_lo)"
         self.keys_lo = keys_lo
@@ -38,7 +38,7 @@ class DeviceTable:
         self.keys, self.cnt = keys, cnt
         self.n = keys.numel()
         self.device = keys.device
-        self.idx64 = int(self.n >= 0xFFFFFFF0)
+        self.idx64 = int(self.n >= 0xFFFFFFF0 or force_idx64)     # 64-bit offsets (tables >= 2^32 entries)
         self.idx_dtype = torch.int64 if self.idx64 else torch.int32
         self.bits = bits if bits is not None else self.L.hm_pick_bucket_bits(self.n)
         self.fbits = fbits if fbits is not None else self.L.hm_pick_filter_bits(self.n)

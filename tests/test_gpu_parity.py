@@ -270,6 +270,28 @@ def test_result_independent_of_bucket_bits_and_work_split():
 
 # ------------------------------------------------------------------ (c) vs the reference binary
 
+@pytest.mark.parametrize("k", [31, 40])
+def test_64bit_offset_kernels_match_32bit(k):
+    """tables with >= 2^32 entries (BASELINE configs[4]: 5e9) use uint64 bucket offsets / partner
+    indices; force those kernel instantiations on a small table and compare with the uint32 ones"""
+    import torch
+    from smudgeplot_b200.device import DeviceTable
+    keys, cnt = synth.synth_table(k, 120000, 3, 0.02, 60, 8, 91, device="cuda")
+    khi = keys[:, 0].contiguous() if k > 32 else keys
+    klo = keys[:, 1].contiguous() if k > 32 else None
+    c16 = cnt.to(torch.int16)
+    a = DeviceTable(k, khi, c16, keys_lo=klo).build_index()
+    b = DeviceTable(k, khi, c16, keys_lo=klo, force_idx64=True).build_index()
+    pa, pb = a.scan().clone(), b.scan().clone()
+    assert b.up.dtype == torch.int64 and b.bucket.dtype == torch.int64
+    assert torch.equal(pa, pb) and int(pa.sum()) > 0
+    assert torch.equal(a.deg[:a.n], b.deg[:b.n])
+    assert torch.equal(a.up.long(), b.up)
+    q = khi[:1000].contiguous()
+    assert torch.equal(a.find(q, klo[:1000].contiguous() if klo is not None else None),
+                       b.find(q, klo[:1000].contiguous() if klo is not None else None))
+
+
 def test_long_kmer_work_split_and_filter_widths():
     """k = 40 (two key words): plot independent of bucket / filter width and of the work split"""
     import torch
