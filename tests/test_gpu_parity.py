@@ -286,7 +286,8 @@ def test_64bit_offset_kernels_match_32bit(k):
     assert b.up.dtype == torch.int64 and b.bucket.dtype == torch.int64
     assert torch.equal(pa, pb) and int(pa.sum()) > 0
     assert torch.equal(a.deg[:a.n], b.deg[:b.n])
-    assert torch.equal(a.up.long(), b.up)
+    one = a.deg[:a.n] == 1                   # (with several partners the recorded one is arbitrary and unused)
+    assert torch.equal(a.up.long()[one], b.up[one])
     q = khi[:1000].contiguous()
     assert torch.equal(a.find(q, klo[:1000].contiguous() if klo is not None else None),
                        b.find(q, klo[:1000].contiguous() if klo is not None else None))
