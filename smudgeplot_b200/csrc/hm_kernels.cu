@@ -724,7 +724,7 @@ pass2_plot_kernel(const uint16_t *__restrict__ cnt, const DegView dv,
   __syncthreads();
   int64_t stride = (int64_t) gridDim.x * blockDim.x;
   for (int64_t i = lo + (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride)
-    { if (((const uint8_t *) dv.self)[i] > 1)
+    { if (((const uint8_t *) dv.self)[i] != 1)     /* 0: no pair at all; >1 (reference: Pair > 1): not isolated */
         continue;
       IdxT j = up[i-lo];
       if (j == IdxNone<IdxT>::value)
