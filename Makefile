@@ -12,7 +12,7 @@ LIBDIR := smudgeplot_b200/lib
 BINDIR := smudgeplot_b200/bin
 OBJDIR := build
 LIB    := $(LIBDIR)/libhetmers_b200.so
-BIN    := $(BINDIR)/hetmers
+BIN    := $(BINDIR)/hetmers $(BINDIR)/extract_kmer_pairs
 
 CU_SRC := smudgeplot_b200/csrc/hm_kernels.cu smudgeplot_b200/csrc/hm_scan.cu smudgeplot_b200/csrc/hm_peer.cu \
           smudgeplot_b200/csrc/hm_condition.cu
@@ -37,9 +37,15 @@ $(LIB): $(CU_OBJ) $(C_OBJ)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) -shared $(ARCH) -o $@ $^ -cudart static -lpthread
 
-$(BIN): smudgeplot_b200/host/hetmers_main.c $(LIB) $(HDRS)
+$(BINDIR)/hetmers: smudgeplot_b200/host/hetmers_main.c $(LIB) $(HDRS)
 	@mkdir -p $(BINDIR)
 	$(CC) $(CFLAGS) -o $@ $< -L$(LIBDIR) -lhetmers_b200 -Wl,-rpath,'$$ORIGIN/../lib'
+
+# the same host source with the pair-listing output stage (the reference ships PloidyList.c,
+# a near copy of PloidyPlot.c, for this)
+$(BINDIR)/extract_kmer_pairs: smudgeplot_b200/host/hetmers_main.c $(LIB) $(HDRS)
+	@mkdir -p $(BINDIR)
+	$(CC) $(CFLAGS) -DEXTRACT_PAIRS -o $@ $< -L$(LIBDIR) -lhetmers_b200 -Wl,-rpath,'$$ORIGIN/../lib'
 
 oracle:
 	$(MAKE) -C oracle

@@ -123,6 +123,23 @@ int hm_k_pass2_plot(const uint16_t *d_cnt, const uint8_t *d_deg, const void *d_u
                     int64_t lo, int64_t hi, unsigned long long *d_plot,
                     const hm_shards *shards, void *stream);
 
+/* extract_kmer_pairs' pass 2 (src/lib/PloidyList.c:425-450,680-705): every isolated pair whose
+ * pixel (sum, min) has a non-zero label in d_pixmap (uint16[HM_PLOT_CELLS], the PLOT array the
+ * reference fills from the .sma file, PloidyList.c:1313-1350) is appended to d_out: the k-mer with
+ * the higher count, the varying position and the other k-mer's base there.  *d_count (zeroed by
+ * the caller) counts all matches, also those beyond `cap`.                                      */
+typedef struct hm_pair_rec
+  { uint64_t key_hi, key_lo;   /* packed k-mer that print_het prints (left aligned words)       */
+    uint32_t smudge;           /* label from the pixmap (index into the .sma smudge list, 1-based) */
+    uint8_t  pos, alt;         /* varying base position; base (0..3 = acgt) of the partner there */
+    uint16_t pad;
+  } hm_pair_rec;
+
+int hm_k_pass2_extract(const uint64_t *d_keys, const uint64_t *d_keys_lo, const uint16_t *d_cnt,
+                       const uint8_t *d_deg, const void *d_up, int idx64, int64_t lo, int64_t hi,
+                       const uint16_t *d_pixmap, hm_pair_rec *d_out, int64_t cap,
+                       unsigned long long *d_count, const hm_shards *shards, void *stream);
+
 /* Device memory that can be mapped by the other ranks of a one-process-per-GPU job (CUDA IPC):
  * hm_dev_alloc gives a zeroed base allocation on the current device, hm_ipc_export its 64-byte
  * handle (send it to the peers with any host transport), hm_ipc_open maps a peer's allocation.
@@ -200,6 +217,9 @@ int  hm_scan_examine(hm_scan *s, int ethresh, int *trim, int *symm);
 int  hm_scan_condition(hm_scan *s, int ethresh, int do_trim, int do_symm, int64_t *nels_out);
 /* both passes; plot: host int64[HM_PLOT_CELLS]; stats optional */
 int  hm_scan_run(hm_scan *s, int64_t *plot, hm_scan_stats *stats);
+/* after hm_scan_run: the pair list of extract_kmer_pairs for a pixel->smudge map (host
+ * uint16[HM_PLOT_CELLS]); *out is malloc'ed (caller frees), sorted by (smudge, k-mer).          */
+int  hm_scan_extract(hm_scan *s, const uint16_t *pixmap, hm_pair_rec **out, int64_t *n_out);
 /* one call: create + run + destroy (what bench.py's e2e leg times) */
 int  hm_hetmers_host(const hm_host_table *t, const int *dev, int n_gpus,
                      int64_t *plot, hm_scan_stats *stats);

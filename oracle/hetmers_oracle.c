@@ -22,6 +22,8 @@
  *     recursion over the in-memory sorted table                               -> oracle_scan
  *   - uint8 incidence array `Pair` with wrap-around (PloidyPlot.c:163,:260-261)
  *   - SMAX/FMAX gates and the .smu writer (PloidyPlot.c:48-49,:1603-1617)      -> oracle_write_smu
+ *   - extract_kmer_pairs: the same pass 2 writing labelled pairs as sequences
+ *     (PloidyList.c:128-165 print_het, :425-450,:680-705, .sma parser :1288-1352) -> oracle_extract_file
  *
  * Works for any k (keys are kept as kbyte-byte big-endian strings), ibyte in {1,2,3}.
  *******************************************************************************************/
@@ -222,7 +224,23 @@ typedef struct
     int             pass1;
     uint8_t        *pair;      /* incidence array, uint8 with wrap (PloidyPlot.c:163) */
     int64_t        *plot;      /* [SMAX+1][FMAX+1] */
+    const uint16_t *pix;       /* extract mode: pixel -> smudge label (PloidyList.c PLOT), else NULL */
+    FILE          **out;       /* extract mode: out[label] */
   } Scan;
+
+/* print_het (PloidyList.c:128-165): the k-mer in lower case with "(x/alt)" at position `half` */
+static void print_het(const uint8_t *seq, int len, int half, int alt, FILE *f)
+{ static const char dna[4] = { 'a', 'c', 'g', 't' };
+  int i;
+  for (i = 0; i < len; i++)
+    { int b = (seq[i>>2] >> (6-2*(i&3))) & 0x3;
+      if (i == half)
+        fprintf(f,"(%c/%c)",dna[b],dna[alt]);
+      else
+        fputc(dna[b],f);
+    }
+  fputc('\n',f);
+}
 
 /* One node of the prefix trie: entries [lo,hi) share their first `level` bases.  Split them by
  * the base at `level` into 4 sorted lists, merge the lists on the remaining suffix, treat every
@@ -279,7 +297,16 @@ static void scan_node(Scan *S, int64_t lo, int64_t hi, int level)
                   for (a = 0; a < i; a++)
                     { int x = cnt[a]+cnt[i];
                       if (x <= SMAX && S->pair[ptr[in[a]]] <= 1)      /* :407 */
-                        S->plot[x*PLOT_W + (cnt[a] < cnt[i] ? cnt[a] : cnt[i])] += 1;
+                        { int mn = (cnt[a] < cnt[i] ? cnt[a] : cnt[i]);
+                          S->plot[x*PLOT_W + mn] += 1;
+                          if (S->pix != NULL && S->pix[x*PLOT_W + mn] > 0)   /* PloidyList.c:431-447 */
+                            { FILE *f = S->out[S->pix[x*PLOT_W + mn]];
+                              if (cnt[a] < cnt[i])
+                                print_het(S->keys + ptr[in[i]]*kb,S->kmer,level,in[a],f);
+                              else
+                                print_het(S->keys + ptr[in[a]]*kb,S->kmer,level,in[i],f);
+                            }
+                        }
                     }
             }
         }
@@ -298,7 +325,7 @@ int oracle_scan(const uint8_t *keys, const uint16_t *cnt, int64_t n, int kmer,
 { Scan S;
 
   S.keys = keys; S.cnt = cnt; S.kmer = kmer; S.kbyte = (kmer+3)>>2;
-  S.plot = plot;
+  S.plot = plot; S.pix = NULL; S.out = NULL;
   S.pair = calloc((size_t) (n > 0 ? n : 1),1);
   if (S.pair == NULL)
     return (-1);
@@ -344,6 +371,70 @@ int oracle_hetmers_file(const char *table, int ethresh, const char *smu_path,
   free(plot);
   oracle_free_table(&T);
   return (rc == 0 ? 0 : 1);
+}
+
+/* extract_kmer_pairs on a conditioned table: parse <sma> (PloidyList.c:1288-1352), open
+ * <out>.<a>A<b>B.txt per smudge, run both passes, write the labelled pairs (traversal order; the
+ * reference's order depends on its thread schedule -- compare sorted).  0 ok, 1 cannot open table
+ * or smudge file, 2 needs conditioning, 3 malformed .sma.                                      */
+int oracle_extract_file(const char *table, int ethresh, const char *sma_path, const char *out_root)
+{ OTable    T;
+  Scan      S;
+  int64_t  *plot;
+  uint16_t *pix;
+  FILE     *f, *out[65536];
+  int       sa[4096], sb[4096], nsm = 0, trim, symm, i, j, a, b, s, pass;
+  char      buf[1000], *name;
+
+  f = fopen(sma_path,"r");
+  if (f == NULL)
+    return (1);
+  pix  = calloc(PLOT_N,sizeof(uint16_t));
+  name = malloc(strlen(out_root)+64);
+  if (fgets(buf,1000,f) == NULL) buf[0] = 0;
+  while (fgets(buf,1000,f) != NULL)
+    { if (sscanf(buf," %d %d %*d %dA%dB",&i,&j,&a,&b) != 4 || a <= 0 || b <= 0 || a < b ||
+          i < 0 || i > FMAX || j < i || i+j > SMAX)
+        { fclose(f); free(pix); free(name); return (3); }
+      for (s = 0; s < nsm; s++)
+        if (sa[s] == a && sb[s] == b)
+          break;
+      if (s >= nsm)
+        { if (nsm >= 4095) { fclose(f); free(pix); free(name); return (3); }
+          sa[s] = a; sb[s] = b;
+          sprintf(name,"%s.%dA%dB.txt",out_root,a,b);
+          out[s+1] = fopen(name,"w");
+          if (out[s+1] == NULL) { fclose(f); free(pix); free(name); return (1); }
+          nsm += 1;
+        }
+      pix[(i+j)*PLOT_W+i] = (uint16_t) (s+1);
+    }
+  fclose(f);
+  free(name);
+
+  if (oracle_load_table(table,&T) != 0)
+    { for (s = 1; s <= nsm; s++) fclose(out[s]);
+      free(pix); return (1);
+    }
+  oracle_examine(&T,ethresh,&trim,&symm);
+  if (!(trim && symm))
+    { for (s = 1; s <= nsm; s++) fclose(out[s]);
+      oracle_free_table(&T); free(pix); return (2);
+    }
+  plot = calloc(PLOT_N,sizeof(int64_t));
+  S.keys = T.keys; S.cnt = T.cnt; S.kmer = T.kmer; S.kbyte = T.kbyte;
+  S.plot = plot; S.pix = NULL; S.out = out;
+  S.pair = calloc((size_t) (T.nels > 0 ? T.nels : 1),1);
+  for (pass = 1; pass >= 0; pass--)
+    { S.pass1 = pass;
+      S.pix   = pass ? NULL : pix;
+      scan_node(&S,0,T.nels,0);
+    }
+  for (s = 1; s <= nsm; s++)
+    fclose(out[s]);
+  free(S.pair); free(plot); free(pix);
+  oracle_free_table(&T);
+  return (0);
 }
 
 #ifdef ORACLE_MAIN

@@ -18,7 +18,7 @@ PLOT_CELLS = (SMAX + 1) * (FMAX + 1)
 ABI_SYMBOLS = [
     "hm_last_error", "hm_abi_version", "hm_device_count", "hm_device_info",
     "hm_k_unpack_records", "hm_k_build_bucket_index", "hm_k_pass1_degree", "hm_k_pass2_plot",
-    "hm_k_min_count", "hm_k_find_keys", "hm_pick_bucket_bits",
+    "hm_k_min_count", "hm_k_find_keys", "hm_pick_bucket_bits", "hm_k_pass2_extract", "hm_scan_extract",
     "hm_k_build_filter", "hm_filter_words", "hm_pick_filter_bits",
     "hm_dev_alloc", "hm_dev_free", "hm_ipc_export", "hm_ipc_open", "hm_ipc_close", "hm_p2p_native_atomics",
     "hm_scan_create", "hm_set_io_threads", "hm_scan_destroy", "hm_scan_examine", "hm_scan_condition", "hm_scan_run", "hm_hetmers_host",
@@ -40,6 +40,12 @@ class Shards(C.Structure):
     """hm_shards: shard offsets + every owner's full-length incidence array as seen from this GPU"""
     _fields_ = [("n_shards", C.c_int32), ("self_", C.c_int32), ("off", C.c_int64 * (MAX_SHARDS + 1)),
                 ("deg", C.c_void_p * MAX_SHARDS)]
+
+
+class PairRec(C.Structure):
+    """hm_pair_rec: one line of extract_kmer_pairs' output"""
+    _fields_ = [("key_hi", C.c_uint64), ("key_lo", C.c_uint64), ("smudge", C.c_uint32),
+                ("pos", C.c_uint8), ("alt", C.c_uint8), ("pad", C.c_uint16)]
 
 
 class ScanStats(C.Structure):
@@ -97,6 +103,7 @@ def lib():
     L.hm_scan_examine.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
     L.hm_scan_condition.argtypes = [vp, i32, i32, i32, C.POINTER(i64)]
     L.hm_scan_run.argtypes = [vp, vp, C.POINTER(ScanStats)]
+    L.hm_scan_extract.argtypes = [vp, vp, C.POINTER(C.POINTER(PairRec)), C.POINTER(i64)]
     L.hm_hetmers_host.argtypes = [C.POINTER(HostTable), C.POINTER(i32), i32, vp, C.POINTER(ScanStats)]
     L.hm_scan_download.argtypes = [vp, vp, vp, vp, vp]
     L.hm_table_open.argtypes = [C.c_char_p, C.POINTER(vp)]

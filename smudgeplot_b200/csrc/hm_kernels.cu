@@ -10,6 +10,7 @@
  *   filter_build_kernel     (none: the merge's "no head has this suffix", PloidyPlot.c:618-643)
  *   pass1_filter_kernel     analysis_in_core_1 / _thread_1     PloidyPlot.c:454-568,:168-301
  *   pass2_plot_kernel       analysis_in_core_2 / _thread_2     PloidyPlot.c:570-700,:303-452
+ *   pass2_extract_kernel    the same in extract_kmer_pairs      PloidyList.c:425-450,:680-705
  *   min_count_kernel        examine_table (trim half)          PloidyPlot.c:1171-1197
  *   find_keys_kernel        GoTo_Kmer_Entry exact-hit use      PloidyPlot.c:1213
  *******************************************************************************************/
@@ -709,6 +710,7 @@ extern "C" int hm_k_pass1_degree(const uint64_t *d_keys, const uint64_t *d_keys_
 #define P2_TM 96       /*                     mins  <  96   (72 KB -> 3 CTAs per SM) */
 #define P2_THREADS 512
 #define P2_CTAS_PER_SM 3
+#define P2_ILP 4
 
 /* deg[x] <= 1 and deg[y] <= 1 for a recorded qualifying pair means both are exactly 1, i.e. the
  * pair is isolated: one count in plot[cx+cy][min].  Persistent CTAs keep the dense corner of the
@@ -722,23 +724,43 @@ pass2_plot_kernel(const uint16_t *__restrict__ cnt, const DegView dv,
   for (int t = threadIdx.x; t < P2_TS*P2_TM; t += blockDim.x)
     tile[t] = 0;
   __syncthreads();
-  int64_t stride = (int64_t) gridDim.x * blockDim.x;
-  for (int64_t i = lo + (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride)
-    { if (((const uint8_t *) dv.self)[i] != 1)     /* 0: no pair at all; >1 (reference: Pair > 1): not isolated */
-        continue;
-      IdxT j = up[i-lo];
-      if (j == IdxNone<IdxT>::value)
-        continue;
-      const uint8_t *dj = (const uint8_t *) deg_words(dv,(int64_t) j);
-      if ((dj == (const uint8_t *) dv.self ? __ldg(dj+j) : __ldcv(dj+j)) > 1)   /* foreign: peer load */
-        continue;
-      int ci = cnt[i], cj = __ldg(cnt+j);
-      int s  = ci+cj;
-      int m  = ci < cj ? ci : cj;
-      if (s < P2_TS && m < P2_TM)
-        atomicAdd(tile + s*P2_TM + m, 1u);
-      else
-        atomicAdd(plot + s*HM_PLOT_W + m, 1ull);
+  /* P2_ILP entries per thread and trip: all their independent loads (degree bytes, partner
+   * indices, then both partner look-ups at once) are in flight together -- the kernel is bound by
+   * the latency of the two dependent gathers, not by bytes or instructions                      */
+  const int64_t stride = (int64_t) gridDim.x * blockDim.x * P2_ILP;
+  for (int64_t i0 = lo + (int64_t) blockIdx.x * blockDim.x * P2_ILP + threadIdx.x; i0 < hi; i0 += stride)
+    { uint8_t di[P2_ILP];
+      IdxT    j[P2_ILP];
+#pragma unroll
+      for (int u = 0; u < P2_ILP; u++)
+        { int64_t i = i0 + (int64_t) u * blockDim.x;
+          di[u] = (i < hi) ? ((const uint8_t *) dv.self)[i] : (uint8_t) 0;
+        }
+#pragma unroll
+      for (int u = 0; u < P2_ILP; u++)       /* 0: no pair at all; >1 (reference: Pair > 1): not isolated */
+        j[u] = (di[u] == 1) ? up[i0 + (int64_t) u * blockDim.x - lo] : IdxNone<IdxT>::value;
+      uint8_t dj[P2_ILP];
+      int     ci[P2_ILP], cj[P2_ILP];
+#pragma unroll
+      for (int u = 0; u < P2_ILP; u++)
+        { dj[u] = 2; ci[u] = cj[u] = 0;
+          if (j[u] != IdxNone<IdxT>::value)
+            { const uint8_t *pj = (const uint8_t *) deg_words(dv,(int64_t) j[u]);
+              dj[u] = (pj == (const uint8_t *) dv.self) ? __ldg(pj+j[u]) : __ldcv(pj+j[u]);  /* foreign: peer load */
+              cj[u] = __ldg(cnt+j[u]);
+              ci[u] = cnt[i0 + (int64_t) u * blockDim.x];
+            }
+        }
+#pragma unroll
+      for (int u = 0; u < P2_ILP; u++)
+        if (dj[u] <= 1)
+          { int s = ci[u]+cj[u];
+            int m = ci[u] < cj[u] ? ci[u] : cj[u];
+            if (s < P2_TS && m < P2_TM)
+              atomicAdd(tile + s*P2_TM + m, 1u);
+            else
+              atomicAdd(plot + s*HM_PLOT_W + m, 1ull);
+          }
     }
   __syncthreads();
   for (int t = threadIdx.x; t < P2_TS*P2_TM; t += blockDim.x)
@@ -769,7 +791,7 @@ extern "C" int hm_k_pass2_plot(const uint16_t *d_cnt, const uint8_t *d_deg, cons
         return hm_cuda_fail(e1 != cudaSuccess ? e1 : e2,"cudaFuncSetAttribute(pass2)");
       configured[dev] = 1;
     }
-  int64_t want = (hi-lo+P2_THREADS-1)/P2_THREADS;
+  int64_t want = (hi-lo+P2_THREADS*P2_ILP-1)/(P2_THREADS*P2_ILP);
   int     grid = (int) (want < sms*P2_CTAS_PER_SM ? want : sms*P2_CTAS_PER_SM);
   DegView dv   = make_deg_view((uint8_t *) d_deg,lo,hi,shards);
   if (idx64)
@@ -781,6 +803,80 @@ extern "C" int hm_k_pass2_plot(const uint16_t *d_cnt, const uint8_t *d_deg, cons
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return hm_cuda_fail(e,"pass2_plot_kernel");
+  return HM_OK;
+}
+
+/* ------------------------------------------------------------- pass 2, extract variant -- */
+
+/* extract_kmer_pairs (src/lib/PloidyList.c): same isolated pairs as pass 2, but instead of
+ * counting pixel (sum, min) the pair is written out when the pixel carries a smudge label
+ * (PLOT[x][min] > 0, PloidyList.c:433-447,688-702).  The k-mer printed is the one with the HIGHER
+ * count (on a tie the one with the smaller base), annotated with the other one's base at the
+ * varying position -- print_het(seq,len,half,alt), PloidyList.c:128-165.                       */
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+pass2_extract_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ keys_lo,
+                     const uint16_t *__restrict__ cnt, const DegView dv,
+                     const IdxT *__restrict__ up, int64_t lo, int64_t hi,
+                     const uint16_t *__restrict__ pixmap, hm_pair_rec *__restrict__ out,
+                     unsigned long long cap, unsigned long long *__restrict__ count)
+{ int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t i = lo + (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride)
+    { if (((const uint8_t *) dv.self)[i] != 1)
+        continue;
+      IdxT j = up[i-lo];
+      if (j == IdxNone<IdxT>::value)
+        continue;
+      const uint8_t *dj = (const uint8_t *) deg_words(dv,(int64_t) j);
+      if ((dj == (const uint8_t *) dv.self ? __ldg(dj+j) : __ldcv(dj+j)) > 1)
+        continue;
+      int ci = cnt[i], cj = __ldg(cnt+j);
+      int s  = ci+cj;
+      int m  = ci < cj ? ci : cj;
+      unsigned pix = pixmap[s*HM_PLOT_W + m];
+      if (pix == 0)
+        continue;
+      uint64_t xh = keys[i], yh = __ldg(keys+j);
+      uint64_t xl = keys_lo ? keys_lo[i] : 0, yl = keys_lo ? __ldg(keys_lo+j) : 0;
+      int pos = (xh != yh) ? (__clzll((long long) (xh ^ yh)) >> 1)
+                           : 32 + (__clzll((long long) (xl ^ yl)) >> 1);
+      int sh  = 62-2*(pos&31);
+      int bi  = (int) (((pos < 32 ? xh : xl) >> sh) & 3);      /* i < j: bi < bj */
+      int bj  = (int) (((pos < 32 ? yh : yl) >> sh) & 3);
+      hm_pair_rec r;
+      if (ci < cj) { r.key_hi = yh; r.key_lo = yl; r.alt = (uint8_t) bi; }   /* PloidyList.c:433-439 */
+      else         { r.key_hi = xh; r.key_lo = xl; r.alt = (uint8_t) bj; }   /*              :441-447 */
+      r.smudge = pix; r.pos = (uint8_t) pos; r.pad = 0;
+      unsigned long long at = atomicAdd(count,1ull);
+      if (at < cap)
+        out[at] = r;
+    }
+}
+
+extern "C" int hm_k_pass2_extract(const uint64_t *d_keys, const uint64_t *d_keys_lo,
+                                  const uint16_t *d_cnt, const uint8_t *d_deg, const void *d_up,
+                                  int idx64, int64_t lo, int64_t hi, const uint16_t *d_pixmap,
+                                  hm_pair_rec *d_out, int64_t cap, unsigned long long *d_count,
+                                  const hm_shards *shards, void *stream)
+{ if (lo > hi || cap < 0)
+    return hm_set_error(HM_EINVAL,"extract: bad range or capacity");
+  if (hi == lo)
+    return HM_OK;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms,cudaDevAttrMultiProcessorCount,dev);
+  int64_t want = (hi-lo+255)/256;
+  int     grid = (int) (want < sms*8 ? want : sms*8);
+  DegView dv   = make_deg_view((uint8_t *) d_deg,lo,hi,shards);
+  if (idx64)
+    pass2_extract_kernel<uint64_t><<<grid,256,0,(cudaStream_t) stream>>>
+        (d_keys,d_keys_lo,d_cnt,dv,(const uint64_t *) d_up,lo,hi,d_pixmap,d_out,(unsigned long long) cap,d_count);
+  else
+    pass2_extract_kernel<uint32_t><<<grid,256,0,(cudaStream_t) stream>>>
+        (d_keys,d_keys_lo,d_cnt,dv,(const uint32_t *) d_up,lo,hi,d_pixmap,d_out,(unsigned long long) cap,d_count);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return hm_cuda_fail(e,"pass2_extract_kernel");
   return HM_OK;
 }
 

@@ -49,6 +49,8 @@ struct hm_scan
     int64_t  n;
     DevTable d[HM_MAX_GPUS];
     double   ms_load, ms_alloc, ms_records, ms_index;
+    int      ran, peer_mode;              /* state of the last hm_scan_run */
+    hm_shards sh[HM_MAX_GPUS];
     int64_t  launches;
   };
 
@@ -483,8 +485,8 @@ extern "C" int hm_scan_run(hm_scan *s, int64_t *plot, hm_scan_stats *stats)
   /* several GPUs: foreign incidence bytes are reached through the owner's array (remote atomics
    * in pass 1, remote loads in pass 2) when every pair of GPUs has native NVLink atomics; otherwise
    * the partial arrays are summed by the peer-memory kernel of hm_peer.cu                        */
-  int       peer_mode = (G > 1);
-  hm_shards sh[HM_MAX_GPUS];
+  int        peer_mode = (G > 1);
+  hm_shards *sh = s->sh;
   for (int a = 0; a < G && peer_mode; a++)
     for (int b = a+1; b < G && peer_mode; b++)
       if (!hm_p2p_native_atomics(s->d[a].dev,s->d[b].dev))
@@ -573,6 +575,7 @@ extern "C" int hm_scan_run(hm_scan *s, int64_t *plot, hm_scan_stats *stats)
       for (int k = 0; k < 4; k++)
         cudaEventDestroy(ev[g][k]);
     }
+  s->ran = 1; s->peer_mode = peer_mode;
   if (stats != NULL)
     { stats->nels = n; stats->n_gpus = G; stats->bucket_bits = s->bits;
       stats->filter_bits = s->fpos; stats->reserved = 0;
@@ -584,6 +587,72 @@ extern "C" int hm_scan_run(hm_scan *s, int64_t *plot, hm_scan_stats *stats)
       stats->ms_alloc = s->ms_alloc; stats->ms_records = s->ms_records; stats->ms_index = s->ms_index;
     }
   (void) launches0;
+  return HM_OK;
+}
+
+static int rec_cmp(const void *a, const void *b)
+{ const hm_pair_rec *x = (const hm_pair_rec *) a, *y = (const hm_pair_rec *) b;
+  if (x->smudge != y->smudge) return (x->smudge < y->smudge ? -1 : 1);
+  if (x->key_hi != y->key_hi) return (x->key_hi < y->key_hi ? -1 : 1);
+  if (x->key_lo != y->key_lo) return (x->key_lo < y->key_lo ? -1 : 1);
+  if (x->pos != y->pos)       return (x->pos < y->pos ? -1 : 1);
+  return ((int) x->alt - (int) y->alt);
+}
+
+/* extract_kmer_pairs' output as a list (PloidyList.c:425-450): needs the incidence array and the
+ * recorded partners of a preceding hm_scan_run.  Two launches per GPU: count, then fill.        */
+extern "C" int hm_scan_extract(hm_scan *s, const uint16_t *pixmap, hm_pair_rec **out, int64_t *n_out)
+{ int G = s->ngpu, rc = HM_OK;
+  if (!s->ran)
+    return hm_set_error(HM_EINVAL,"hm_scan_extract needs a preceding hm_scan_run");
+  int64_t      total = 0, cnts[HM_MAX_GPUS];
+  hm_pair_rec *d_out[HM_MAX_GPUS];
+  uint16_t    *d_pix[HM_MAX_GPUS];
+  unsigned long long *d_cnt[HM_MAX_GPUS];
+  memset(d_out,0,sizeof(d_out)); memset(d_pix,0,sizeof(d_pix)); memset(d_cnt,0,sizeof(d_cnt));
+  for (int pass = 0; pass < 2 && rc == HM_OK; pass++)
+    { for (int g = 0; g < G && rc == HM_OK; g++)
+        { DevTable *D = s->d+g;
+          HM_CUDA(cudaSetDevice(D->dev));
+          if (pass == 0)
+            { HM_CUDA(cudaMalloc(&d_pix[g],sizeof(uint16_t)*HM_PLOT_CELLS));
+              HM_CUDA(cudaMalloc(&d_cnt[g],sizeof(unsigned long long)));
+              HM_CUDA(cudaMemcpyAsync(d_pix[g],pixmap,sizeof(uint16_t)*HM_PLOT_CELLS,cudaMemcpyHostToDevice,D->st));
+            }
+          else if (cnts[g] > 0)
+            HM_CUDA(cudaMalloc(&d_out[g],sizeof(hm_pair_rec)*(size_t) cnts[g]));
+          HM_CUDA(cudaMemsetAsync(d_cnt[g],0,sizeof(unsigned long long),D->st));
+          rc = hm_k_pass2_extract(D->keys,D->keys_lo,D->cnt,D->deg,D->up,s->idx64,D->lo,D->hi,d_pix[g],
+                                  d_out[g],pass == 0 ? 0 : cnts[g],d_cnt[g],s->peer_mode ? &s->sh[g] : NULL,D->st);
+          s->launches += (D->hi > D->lo);
+        }
+      for (int g = 0; g < G && rc == HM_OK; g++)
+        { unsigned long long c = 0;
+          HM_CUDA(cudaSetDevice(s->d[g].dev));
+          HM_CUDA(cudaMemcpyAsync(&c,d_cnt[g],sizeof(c),cudaMemcpyDeviceToHost,s->d[g].st));
+          HM_CUDA(cudaStreamSynchronize(s->d[g].st));
+          if (pass == 0) { cnts[g] = (int64_t) c; total += cnts[g]; }
+        }
+    }
+  hm_pair_rec *host = (hm_pair_rec *) malloc(sizeof(hm_pair_rec)*(size_t) (total > 0 ? total : 1));
+  if (host == NULL && rc == HM_OK)
+    rc = hm_set_error(HM_ENOMEM,"out of host memory for %lld pair records",(long long) total);
+  int64_t at = 0;
+  for (int g = 0; g < G; g++)
+    { cudaSetDevice(s->d[g].dev);
+      if (rc == HM_OK && cnts[g] > 0)
+        { cudaError_t e = cudaMemcpy(host+at,d_out[g],sizeof(hm_pair_rec)*(size_t) cnts[g],cudaMemcpyDeviceToHost);
+          if (e != cudaSuccess) rc = hm_cuda_fail(e,"cudaMemcpy(pair records)");
+          at += cnts[g];
+        }
+      if (d_out[g]) cudaFree(d_out[g]);
+      if (d_pix[g]) cudaFree(d_pix[g]);
+      if (d_cnt[g]) cudaFree(d_cnt[g]);
+    }
+  if (rc != HM_OK)
+    { free(host); return rc; }
+  qsort(host,(size_t) total,sizeof(hm_pair_rec),rec_cmp);      /* deterministic order */
+  *out = host; *n_out = total;
   return HM_OK;
 }
 

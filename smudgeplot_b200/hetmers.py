@@ -59,6 +59,32 @@ def run_hetmers(infile, o="smudgeplot", L=None, t=4, verbose=False, tmp=".", gpu
     return f"{o}.smu"
 
 
+def extract_args(infile, sma, o="kmerpairs", t=4, verbose=False, tmp="."):
+    """argv tail of `smudgeplot extract` exactly as cli.py:368-378 builds it"""
+    args = [f"-o{o}", f"-T{t}"]
+    if verbose:
+        args.append("-v")
+    if tmp != ".":
+        args.append(f"-P{tmp}")
+    args.append(str(infile))
+    s = str(sma)
+    args.append(s[:-4] if s.endswith(".sma") else s)
+    return args
+
+
+def run_extract(infile, sma, o="kmerpairs", t=4, verbose=False, tmp=".", gpus=None, e=None):
+    """Spawn our `extract_kmer_pairs` (same boundary as the reference's second binary,
+    src/lib/PloidyList.c; cli.py:368-382).  Writes <o>.<a>A<b>B.txt per smudge of the .sma."""
+    cmd = [get_binary_path("extract_kmer_pairs")] + extract_args(infile, sma, o, t, verbose, tmp)
+    if e is not None:
+        cmd.insert(1, f"-e{e}")
+    sys.stderr.write(f"Calling: {shlex.join(cmd)}\n")
+    env = dict(os.environ)
+    if gpus is not None:
+        env["HETMERS_GPUS"] = str(gpus)
+    subprocess.run(cmd, check=True, env=env)
+
+
 # ------------------------------------------------------------------ in-process (C ABI layer B) --
 
 def _host_table(kt: KtabFiles):
@@ -107,6 +133,24 @@ class Scan:
         st = _lib.ScanStats()
         _lib.check(self._L.hm_scan_run(self._h, plot.ctypes.data, C.byref(st)))
         return plot.reshape(_lib.SMAX + 1, _lib.PLOT_W), st.as_dict()
+
+    def extract(self, pixmap: np.ndarray):
+        """pair list of extract_kmer_pairs (after run()): pixmap uint16[1001,501], label 0 = none;
+        -> structured array (key_hi, key_lo, smudge, pos, alt) sorted by (smudge, k-mer)"""
+        pm = np.ascontiguousarray(pixmap, dtype=np.uint16).reshape(-1)
+        assert pm.size == _lib.PLOT_CELLS
+        out = C.POINTER(_lib.PairRec)()
+        n = C.c_int64()
+        _lib.check(self._L.hm_scan_extract(self._h, pm.ctypes.data, C.byref(out), C.byref(n)))
+        dt = np.dtype([("key_hi", "<u8"), ("key_lo", "<u8"), ("smudge", "<u4"), ("pos", "u1"), ("alt", "u1"),
+                       ("pad", "<u2")])
+        arr = np.empty(n.value, dtype=dt)
+        if n.value:
+            C.memmove(arr.ctypes.data, out, n.value * dt.itemsize)
+        libc = C.CDLL(None)
+        libc.free.argtypes = [C.c_void_p]
+        libc.free(out)
+        return arr
 
     def download(self, deg: bool = True):
         n = getattr(self, "nels", self.kt.nels)

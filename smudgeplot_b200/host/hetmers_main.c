@@ -28,10 +28,24 @@ static double wall_ms(void)
   return ts.tv_sec*1e3 + ts.tv_nsec*1e-6;
 }
 
+/* Compiled twice: plain -> `hetmers` (PloidyPlot.c), with -DEXTRACT_PAIRS -> `extract_kmer_pairs`
+ * (src/lib/PloidyList.c:1207-1583: same search, but the isolated pairs whose (covB,covA) pixel is
+ * labelled in <smudges>.sma are written as sequences to <out>.<a>A<b>B.txt instead of counted). */
+#ifdef EXTRACT_PAIRS
+static const char *Prog_Name = "extract_kmer_pairs";
+
+static const char *Usage[] = { " [-v] [-T<int(4)>] [-P<dir(/tmp)>]",
+                               " [-o<output>] [-e<int(4)>] <source>[.ktab] <smudges>[.sma]" };
+#define NPOSITIONAL 3
+
+typedef struct { int a, b; FILE *f; } Smudge;
+#else
 static const char *Prog_Name = "hetmers";
 
 static const char *Usage[] = { " [-v] [-T<int(4)>] [-P<dir(/tmp)>]",
                                " [-o<output>] [-e<int(4)>] <source>[.ktab]" };
+#define NPOSITIONAL 2
+#endif
 
 static int positive_arg(const char *arg, const char *what)      /* ARG_POSITIVE, gene_core.h:46-56 */
 { char *eptr;
@@ -135,7 +149,7 @@ int main(int argc, char *argv[])
 
   VERBOSE = flags['v'];
 
-  if (argc != 2)
+  if (argc != NPOSITIONAL)
     { fprintf(stderr,"\nUsage: %s %s\n",Prog_Name,Usage[0]);
       fprintf(stderr,"       %*s %s\n",(int) strlen(Prog_Name),"",Usage[1]);
       fprintf(stderr,"\n");
@@ -159,6 +173,72 @@ int main(int argc, char *argv[])
         OUT[n-5] = '\0';
     }
 
+#ifdef EXTRACT_PAIRS
+  //  Read in the .sma file: pixel -> smudge map and one output file per smudge (PloidyList.c:1288-1352)
+
+  uint16_t *PIXMAP = calloc(HM_PLOT_CELLS,sizeof(uint16_t));
+  Smudge   *SMUDGE;
+  int       SM_NUM = 0;
+  { char *SMA = strdup(argv[2]);
+    size_t n = strlen(SMA);
+    char  *name, buf[1000];
+    FILE  *f;
+    int    pi, pj, a, b, sidx, nmax = 100;
+
+    if (n > 4 && strcasecmp(SMA+n-4,".sma") == 0)          /* PathnRoot(argv[2],".sma") */
+      SMA[n-4] = '\0';
+    name = malloc(strlen(SMA)+strlen(OUT)+64);
+    sprintf(name,"%s.sma",SMA);
+    f = fopen(name,"r");
+    if (f == NULL)
+      { fprintf(stderr,"\n%s: Could not open smudge file %s.sma",Prog_Name,SMA);
+        exit (1);
+      }
+    SMUDGE = malloc(nmax*sizeof(Smudge));
+    if (PIXMAP == NULL || SMUDGE == NULL)
+      exit (1);
+    if (fgets(buf,1000,f) == NULL)                           /* header line */
+      buf[0] = '\0';
+    while (fgets(buf,1000,f) != NULL)
+      { if (sscanf(buf," %d %d %*d %dA%dB",&pi,&pj,&a,&b) != 4)
+          { fprintf(stderr,"%s: Cannot parse line '%s'\n",Prog_Name,buf);
+            exit (1);
+          }
+        if (a <= 0 || b <= 0 || a < b)
+          { fprintf(stderr,"%s: %dA%dB is not a valid smudge label'\n",Prog_Name,a,b);
+            exit (1);
+          }
+        if (pi < 0 || pi > HM_FMAX || pj < pi || pi+pj > HM_SMAX)
+          { fprintf(stderr,"%s: (%d,%d) is not a valid pixel coordinate\n",Prog_Name,pi,pj);
+            exit (1);
+          }
+        for (sidx = 0; sidx < SM_NUM; sidx++)
+          if (SMUDGE[sidx].a == a && SMUDGE[sidx].b == b)
+            break;
+        if (sidx >= SM_NUM)
+          { if (SM_NUM >= nmax)
+              { nmax += 100;
+                SMUDGE = realloc(SMUDGE,nmax*sizeof(Smudge));
+                if (SMUDGE == NULL)
+                  exit (1);
+              }
+            SMUDGE[sidx].a = a;
+            SMUDGE[sidx].b = b;
+            sprintf(name,"%s.%dA%dB.txt",OUT,a,b);
+            SMUDGE[sidx].f = fopen(name,"w");
+            if (SMUDGE[sidx].f == NULL)
+              { fprintf(stderr,"%s: Cannot open smudge file %s.%dA%dB.txt\n",Prog_Name,OUT,a,b);
+                exit (1);
+              }
+            SM_NUM += 1;
+          }
+        PIXMAP[(pi+pj)*HM_PLOT_W+pi] = (uint16_t) (sidx+1);
+      }
+    fclose(f);
+    free(name);
+    free(SMA);
+  }
+#else
   //  If appropriately named het-mer table found then ask if reuse (PloidyPlot.c:1318-1337)
 
   { char *smu = malloc(strlen(OUT)+8);
@@ -186,6 +266,8 @@ int main(int argc, char *argv[])
         fclose(f);
       }
   }
+
+#endif
 
   //  Open input table and see if it needs conditioning (PloidyPlot.c:1341-1426)
 
@@ -320,6 +402,13 @@ int main(int argc, char *argv[])
   if (hm_scan_run(S,PLOT,&stats) != HM_OK)
     die_hm();
   t_scan = wall_ms();
+#ifdef EXTRACT_PAIRS
+  hm_pair_rec *REC = NULL;
+  int64_t      NREC = 0;
+  int          KMER = hm_table_view(T)->kmer;
+  if (hm_scan_extract(S,PIXMAP,&REC,&NREC) != HM_OK)
+    die_hm();
+#endif
   hm_scan_destroy(S);
   hm_table_close(T);
 
@@ -343,6 +432,31 @@ int main(int argc, char *argv[])
       free(input);
     }
 
+#ifdef EXTRACT_PAIRS
+  //  The pair list comes back sorted by (smudge, k-mer); one line per pair in print_het's format
+  //  (PloidyList.c:128-165): lower-case bases with "(x/y)" at the varying position
+  { static const char dna[4] = { 'a', 'c', 'g', 't' };
+    char   line[160];
+    int64_t r;
+    for (r = 0; r < NREC; r++)
+      { const hm_pair_rec *q = REC+r;
+        char *o = line;
+        int   p;
+        for (p = 0; p < KMER; p++)
+          { int bse = (int) (((p < 32 ? q->key_hi : q->key_lo) >> (62-2*(p&31))) & 3);
+            if (p == q->pos)
+              { *o++ = '('; *o++ = dna[bse]; *o++ = '/'; *o++ = dna[q->alt & 3]; *o++ = ')'; }
+            else
+              *o++ = dna[bse];
+          }
+        *o++ = '\n'; *o = '\0';
+        fputs(line,SMUDGE[q->smudge-1].f);
+      }
+    for (i = 0; i < SM_NUM; i++)
+      fclose(SMUDGE[i].f);
+    free(REC);
+  }
+#else
   if (VERBOSE)
     { fprintf(stderr,"\n  Count complete, outputting table\n");
       fflush(stderr);
@@ -356,6 +470,8 @@ int main(int argc, char *argv[])
       }
     free(smu);
   }
+
+#endif
 
   free(PLOT);
   free(OUT);

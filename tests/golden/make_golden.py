@@ -24,6 +24,25 @@ from smudgeplot_b200 import fastk  # noqa: E402
 from tools import synth  # noqa: E402
 
 REF = os.path.join(ROOT, "oracle", "_ref", "hetmers")
+REF_EXTRACT = os.path.join(ROOT, "oracle", "_ref", "extract_kmer_pairs")
+EXTRACT_CASES = ("dip_k21", "dip_k40", "tet_k32")      # golden pair lists (extract_kmer_pairs)
+
+
+def write_sma(path, smu_text):
+    """label the pixels of a .smu the way `smudgeplot all` writes <o>.sma (cli.py:451-456):
+    header + "covB covA freq <a>A<b>B"; labels here are synthetic (by sum mod 3), one third unlabelled"""
+    with open(path, "w") as f:
+        f.write("covB\tcovA\tfreq\tsmudge\n")
+        for ln in smu_text.splitlines():
+            m, rest, cnt = (int(v) for v in ln.split("\t"))
+            lab = {0: "1A1B", 1: "2A1B"}.get((m + rest) % 3)
+            if lab:
+                f.write(f"{m}\t{rest}\t{cnt}\t{lab}\n")
+
+
+def run_ref_extract(table, sma, out, e, threads=1):
+    return subprocess.run([REF_EXTRACT, f"-e{e}", f"-T{threads}", f"-o{out}", table, sma],
+                          capture_output=True, text=True)
 
 # name -> generator parameters (+ file layout, -e threshold handed to the reference)
 CASES = {
@@ -70,6 +89,30 @@ def main():
         meta[name] = dict(c, nels=int(keys.shape[0]), smu_rows=len(outs[0].splitlines()),
                           verbose=[ln.strip() for ln in r.stderr.splitlines() if "input table" in ln])
         print(name, meta[name]["nels"], "entries,", meta[name]["smu_rows"], "rows")
+        if name in EXTRACT_CASES:
+            # extract_kmer_pairs: the reference's line order depends on its thread schedule, so the
+            # golden files hold the SORTED lines of each <out>.<a>A<b>B.txt (-T1 and -T4 must agree)
+            sma = os.path.join(d, name + ".sma")
+            write_sma(sma, outs[0])
+            lists = []
+            for T in (1, 4):
+                for old in os.listdir(d):
+                    if old.startswith("refx."):
+                        os.remove(os.path.join(d, old))
+                r = run_ref_extract(table, sma, os.path.join(d, "refx"), c["e"], T)
+                assert r.returncode == 0, r.stderr
+                lists.append({f: sorted(open(os.path.join(d, f)).read().splitlines())
+                              for f in sorted(os.listdir(d)) if f.startswith("refx.")})
+            assert lists[0] == lists[1] and lists[0], f"{name}: extract output depends on -T ?"
+            npairs = {}
+            for f, lines in lists[0].items():
+                os.remove(os.path.join(d, f))
+                lab = f[len("refx."):-len(".txt")]
+                with open(os.path.join(d, f"{name}.pairs.{lab}.txt"), "w") as g:
+                    g.write("".join(ln + "\n" for ln in lines))
+                npairs[lab] = len(lines)
+            meta[name]["pairs"] = npairs
+            print("   extract:", npairs)
 
     # conditioning decisions (examine_table, PloidyPlot.c:1167-1230): the reference prints its
     # verdict with -v and then dies trying to run the absent FastK tools Logex / Symmex.

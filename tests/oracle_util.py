@@ -27,8 +27,37 @@ def oracle_lib():
         L.oracle_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
         L.oracle_hetmers_file.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_int),
                                           C.POINTER(C.c_int), C.POINTER(C.c_int64)]
+        L.oracle_extract_file.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_char_p]
         _lib = L
     return _lib
+
+
+REF_EXTRACT = os.path.join(ROOT, "oracle", "_ref", "extract_kmer_pairs")
+
+
+def oracle_extract(table: str, ethresh: int, sma: str, out_root: str) -> int:
+    """oracle restatement of extract_kmer_pairs; 0 ok / 1 cannot open / 2 needs conditioning / 3 bad .sma"""
+    return oracle_lib().oracle_extract_file(table.encode(), ethresh, sma.encode(), out_root.encode())
+
+
+def have_ref_extract():
+    return os.path.exists(REF_EXTRACT) and os.access(REF_EXTRACT, os.X_OK)
+
+
+def run_ref_extract(table: str, sma: str, out_root: str, ethresh: int, threads: int = 4):
+    return subprocess.run([REF_EXTRACT, f"-e{ethresh}", f"-T{threads}", f"-o{out_root}", table, sma],
+                          capture_output=True, text=True)
+
+
+def sorted_pair_files(out_root: str):
+    """{label: sorted lines} of every <out_root>.<a>A<b>B.txt (the reference's line order depends on its
+    thread schedule, so pair lists are compared as sorted multisets)"""
+    d, base = os.path.split(out_root)
+    res = {}
+    for f in sorted(os.listdir(d or ".")):
+        if f.startswith(base + ".") and f.endswith(".txt"):
+            res[f[len(base) + 1:-4]] = sorted(open(os.path.join(d or ".", f)).read().splitlines())
+    return res
 
 
 def oracle_scan(keys_bytes: np.ndarray, cnt: np.ndarray, kmer: int):

@@ -80,6 +80,34 @@ def test_missing_part_file_is_reported(built, tmp_path):
     assert r.returncode == 1 and "Table part" in r.stderr and "is missing ?" in r.stderr
 
 
+def run_x(*args):
+    exe = os.path.join(os.path.dirname(_lib.BIN_PATH), "extract_kmer_pairs")
+    return subprocess.run([exe, *args], capture_output=True, text=True)
+
+
+def test_extract_kmer_pairs_cli_contract(built, tmp_path):
+    """argv / .sma parsing / messages of PloidyList.c:1207-1352 (cases that need no GPU)"""
+    r = run_x("only_one")
+    assert r.returncode == 1 and r.stderr.startswith("\nUsage: extract_kmer_pairs  [-v] [-T<int(4)>] [-P<dir(/tmp)>]\n")
+    assert "<source>[.ktab] <smudges>[.sma]" in r.stderr
+    r = run_x(f"-o{tmp_path}/o", "tab", str(tmp_path / "missing"))
+    assert (r.returncode, r.stderr) == (1, f"\nextract_kmer_pairs: Could not open smudge file {tmp_path}/missing.sma")
+    sma = tmp_path / "s.sma"
+    for body, msg in (("5\t9\t3\tAB\n", "extract_kmer_pairs: Cannot parse line '5\t9\t3\tAB\n'\n"),
+                      ("5\t9\t3\t1A2B\n", "extract_kmer_pairs: 1A2B is not a valid smudge label'\n"),
+                      ("9\t5\t3\t1A1B\n", "extract_kmer_pairs: (9,5) is not a valid pixel coordinate\n")):
+        sma.write_text("covB\tcovA\tfreq\tsmudge\n" + body)
+        r = run_x(f"-o{tmp_path}/o", "tab", str(sma))
+        assert (r.returncode, r.stderr) == (1, msg)
+    # a good .sma: the per-smudge files are created before the table is opened, like the reference
+    sma.write_text("covB\tcovA\tfreq\tsmudge\n5\t9\t3\t1A1B\n6\t9\t1\t2A1B\n7\t9\t1\t1A1B\n")
+    r = run_x(f"-o{tmp_path}/o", str(tmp_path / "absent"), str(tmp_path / "s"))
+    assert (r.returncode, r.stderr) == (1, f"extract_kmer_pairs: Cannot open k-mer table {tmp_path}/absent\n")
+    assert sorted(f.name for f in tmp_path.glob("o.*.txt")) == ["o.1A1B.txt", "o.2A1B.txt"]
+    assert hetmers.extract_args("t.ktab", "x.sma", o="kp", t=8, verbose=True, tmp="/s") == \
+        ["-okp", "-T8", "-v", "-P/s", "t.ktab", "x"]                                   # cli.py:368-378
+
+
 def test_cli_argv_mirror_of_reference_cli():
     # cli.py:350-359
     assert hetmers.hetmers_args("t.ktab", o="out", L=12, t=4) == ["-oout", "-e12", "-T4", "t.ktab"]

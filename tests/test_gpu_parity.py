@@ -72,6 +72,69 @@ def test_default_output_root_and_ktab_suffix(tmp_path):
     assert r.returncode == 0 and "Found het-table" in r.stdout
 
 
+# ------------------------------------------------------------------ extract_kmer_pairs -------
+
+def _golden_pairs(name):
+    d = os.path.join(GOLDEN, name)
+    pre = name + ".pairs."
+    return {f[len(pre):-4]: open(os.path.join(d, f)).read().splitlines()
+            for f in sorted(os.listdir(d)) if f.startswith(pre)}
+
+
+@pytest.mark.parametrize("name", [n for n in golden_cases() if os.path.exists(os.path.join(GOLDEN, n, n + ".sma"))])
+def test_extract_executable_reproduces_reference_pair_lists(name, golden_meta, tmp_path):
+    c = golden_meta[name]
+    out = str(tmp_path / "kp")
+    hetmers.run_extract(_golden(name), _golden(name) + ".sma", o=out, t=4, e=c["e"])
+    assert ou.sorted_pair_files(out) == _golden_pairs(name)
+
+
+@pytest.mark.parametrize("k,G,ploidy,seed,L", [(31, 400000, 3, 41, 12), (40, 150000, 2, 42, 4)])
+def test_extract_matches_reference_binary_and_inprocess_list(k, G, ploidy, seed, L, tmp_path):
+    """bigger seeded table: our extract_kmer_pairs vs the reference's (sorted lines), and the
+    in-process pair list (hm_scan_extract) vs the files"""
+    keys, cnt = synth.synth_table(k, G, ploidy, 0.02, 20 * ploidy, L, seed, device="cuda")
+    name = str(tmp_path / "t")
+    kt = synth.write_table(name, k, keys, cnt, ibyte=3, nparts=3)
+    with hetmers.Scan(kt) as sc:
+        plot, _ = sc.run()
+        s_idx, m_idx = np.nonzero(plot[:, :_lib.FMAX] > 0)
+        pix = np.zeros((_lib.SMAX + 1, _lib.PLOT_W), dtype=np.uint16)
+        labels = ["1A1B", "2A1B", "2A2B"]
+        sma = str(tmp_path / "ann.sma")
+        with open(sma, "w") as f:
+            f.write("covB\tcovA\tfreq\tsmudge\n")
+            order = []
+            for s, m in zip(s_idx.tolist(), m_idx.tolist()):
+                lab = (s + m) % 4
+                if lab < 3:
+                    if labels[lab] not in order:
+                        order.append(labels[lab])
+                    pix[s, m] = order.index(labels[lab]) + 1
+                    f.write(f"{m}\t{s - m}\t{plot[s, m]}\t{labels[lab]}\n")
+        rec = sc.extract(pix)
+    assert len(rec) == int(plot[pix > 0].sum())                       # one record per labelled isolated pair
+    out = str(tmp_path / "kp")
+    hetmers.run_extract(name, sma, o=out, t=4, e=L)
+    ours = ou.sorted_pair_files(out)
+    assert sum(len(v) for v in ours.values()) == len(rec)
+    dna = "acgt"
+    def fmt(r):
+        bases = [((int(r["key_hi"]) if p < 32 else int(r["key_lo"])) >> (62 - 2 * (p & 31))) & 3 for p in range(k)]
+        return "".join(f"({dna[b]}/{dna[int(r['alt'])]})" if p == int(r["pos"]) else dna[b] for p, b in enumerate(bases))
+    mine = {}
+    for r in rec[:: max(1, len(rec) // 2000)]:                        # spot-check the in-process records
+        assert fmt(r) in ours[order[int(r["smudge"]) - 1]]
+    if ou.have_ref_extract():
+        rr = ou.run_ref_extract(name, sma, str(tmp_path / "ref"), L, threads=min(os.cpu_count() or 4, 64))
+        assert rr.returncode == 0, rr.stderr
+        assert ou.sorted_pair_files(str(tmp_path / "ref")) == ours
+    else:
+        assert ou.oracle_extract(name, L, sma, str(tmp_path / "ora")) == 0
+        assert ou.sorted_pair_files(str(tmp_path / "ora")) == ours
+    del mine
+
+
 # ------------------------------------------------------------------ conditioning verdicts ----
 
 @pytest.mark.parametrize("name,verdict,tool", [("untrimmed", (False, True), "Logex"),

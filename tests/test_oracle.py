@@ -23,6 +23,36 @@ def test_oracle_reproduces_reference_smu(name, golden_meta, tmp_path):
     assert len(want.splitlines()) == c["smu_rows"]
 
 
+def _golden_pairs(name):
+    d = os.path.join(GOLDEN, name)
+    pre = name + ".pairs."
+    return {f[len(pre):-4]: open(os.path.join(d, f)).read().splitlines()
+            for f in sorted(os.listdir(d)) if f.startswith(pre)}
+
+
+@pytest.mark.parametrize("name", [n for n in golden_cases() if os.path.exists(os.path.join(GOLDEN, n, n + ".sma"))])
+def test_oracle_extract_reproduces_reference_pair_lists(name, golden_meta, tmp_path):
+    """extract_kmer_pairs (PloidyList.c): the oracle's pair lists == the reference binary's (sorted)"""
+    c = golden_meta[name]
+    want = _golden_pairs(name)
+    assert want and {k: len(v) for k, v in want.items()} == c["pairs"]
+    out = str(tmp_path / "ex")
+    assert ou.oracle_extract(os.path.join(GOLDEN, name, name), c["e"], os.path.join(GOLDEN, name, name + ".sma"), out) == 0
+    assert ou.sorted_pair_files(out) == want
+    k = c["k"]
+    for lines in want.values():                        # print_het format: k bases + "(x/y)" at one position
+        assert all(len(ln) == k + 4 and ln.count("(") == 1 and ln[ln.index("(") + 2] == "/" for ln in lines)
+
+
+def test_oracle_extract_error_codes(tmp_path):
+    sma = tmp_path / "s.sma"
+    sma.write_text("covB\tcovA\tfreq\tsmudge\n5\t9\t3\t1A1B\n")
+    assert ou.oracle_extract(str(tmp_path / "absent"), 4, str(sma), str(tmp_path / "o")) == 1
+    assert ou.oracle_extract(os.path.join(GOLDEN, "dip_k21", "dip_k21"), 4, str(tmp_path / "no.sma"), str(tmp_path / "o")) == 1
+    sma.write_text("covB\tcovA\tfreq\tsmudge\n9\t5\t3\t1A1B\n")          # covB > covA: invalid pixel
+    assert ou.oracle_extract(os.path.join(GOLDEN, "dip_k21", "dip_k21"), 4, str(sma), str(tmp_path / "o")) == 3
+
+
 @pytest.mark.parametrize("name,trim,symm", [("untrimmed", 0, 1), ("asymmetric", 1, 0)])
 def test_oracle_examine_matches_reference_verdict(name, trim, symm, golden_meta, tmp_path):
     c = golden_meta["_conditioning"][name]
