@@ -410,7 +410,9 @@ def measure_e2e(args, torch, dist, dev, multi, world, rank, job, tabl):
             "h2d_bytes_per_step": int(h_rec.numel() + h_idx.numel() * 8),
             "d2h_bytes_per_step": int(_lib.PLOT_CELLS * 8),
             "api": "hm_hetmers_host(hm_host_table in pinned host memory) -> int64 plot[1001*501]",
-            "last_call_ms": {"load": st.ms_h2d_unpack, "pass1": st.ms_pass1, "pass2": st.ms_pass2},
+            "last_call_ms": {"load": st.ms_h2d_unpack, "load_alloc": st.ms_alloc, "load_records": st.ms_records,
+                             "load_index": st.ms_index, "pass1": st.ms_pass1, "pass2": st.ms_pass2, "scan": st.ms_scan,
+                             "total_in_call": st.ms_total},
             "kernel_launches_per_call": int(st.kernel_launches)}
 
 

@@ -273,9 +273,9 @@ extern "C" int hm_k_unpack_records(const uint8_t *d_rec, int64_t n, int64_t firs
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
 bucket_index_kernel(const uint64_t *__restrict__ keys, int64_t n, int bshift, int64_t nbuckets,
-                    IdxT *__restrict__ bucket)
-{ int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > n)
+                    IdxT *__restrict__ bucket, int64_t i0, int64_t i1)
+{ int64_t i = i0 + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;     /* entries [i0,i1]; i == n is the end mark */
+  if (i > i1 || i > n)
     return;
   int64_t cur  = (i < n) ? (int64_t) (keys[i] >> bshift) : nbuckets;
   int64_t prev = (i > 0) ? (int64_t) (keys[i-1] >> bshift) : -1;
@@ -283,24 +283,33 @@ bucket_index_kernel(const uint64_t *__restrict__ keys, int64_t n, int bshift, in
     bucket[b] = (IdxT) i;
 }
 
-extern "C" int hm_k_build_bucket_index(const uint64_t *d_keys, int64_t n, int bits,
-                                       void *d_bucket, int idx64, void *stream)
+/* entries [i0,i1) of a table whose entries [0,i1) are in place (+ the end mark when i1 == n): lets
+ * the loader index every chunk right behind its unpack instead of in a pass of its own         */
+int hm_build_bucket_index_range(const uint64_t *d_keys, int64_t n, int bits, void *d_bucket,
+                                int idx64, int64_t i0, int64_t i1, void *stream)
 { if (bits < 1 || bits > 30)
     return hm_set_error(HM_EINVAL,"bucket bits %d out of range 1..30",bits);
   if (!idx64 && n >= 0xFFFFFFFFll)
     return hm_set_error(HM_EINVAL,"32-bit offsets need n < 2^32-1");
-  int64_t nblk = (n+1+255)/256;
+  int64_t last = (i1 >= n) ? n : i1-1;
+  if (last < i0)
+    return HM_OK;
+  int64_t nblk = (last-i0+1+255)/256;
   if (idx64)
     bucket_index_kernel<uint64_t><<<(unsigned) nblk,256,0,(cudaStream_t) stream>>>
-        (d_keys,n,64-bits,(int64_t) 1<<bits,(uint64_t *) d_bucket);
+        (d_keys,n,64-bits,(int64_t) 1<<bits,(uint64_t *) d_bucket,i0,last);
   else
     bucket_index_kernel<uint32_t><<<(unsigned) nblk,256,0,(cudaStream_t) stream>>>
-        (d_keys,n,64-bits,(int64_t) 1<<bits,(uint32_t *) d_bucket);
+        (d_keys,n,64-bits,(int64_t) 1<<bits,(uint32_t *) d_bucket,i0,last);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return hm_cuda_fail(e,"bucket_index_kernel");
   return HM_OK;
 }
+
+extern "C" int hm_k_build_bucket_index(const uint64_t *d_keys, int64_t n, int bits,
+                                       void *d_bucket, int idx64, void *stream)
+{ return hm_build_bucket_index_range(d_keys,n,bits,d_bucket,idx64,0,n,stream); }
 
 /* ------------------------------------------------------------------ prefix filter ------- */
 
@@ -309,9 +318,9 @@ extern "C" int hm_k_build_bucket_index(const uint64_t *d_keys, int64_t n, int bi
  * the table -- 99 % of all probes -- is answered by one 4-byte load that neighbouring lanes
  * share, instead of a bucket lookup + bisection.                                              */
 __global__ void __launch_bounds__(256)
-filter_build_kernel(const uint64_t *__restrict__ keys, int64_t n, int fshift,
+filter_build_kernel(const uint64_t *__restrict__ keys, int64_t i0, int64_t n, int fshift,
                     uint32_t *__restrict__ filter)
-{ int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+{ int64_t i = i0 + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;     /* entries [i0,n) */
   if (i >= n)
     return;
   uint64_t pf = keys[i] >> fshift;
@@ -320,6 +329,9 @@ filter_build_kernel(const uint64_t *__restrict__ keys, int64_t n, int fshift,
     return;
   atomicOr(filter + (pf>>5), 1u << (pf & 31));
 }
+
+int hm_build_filter_range(const uint64_t *d_keys, int filter_bits, uint32_t *d_filter,
+                          int64_t i0, int64_t i1, void *stream);
 
 extern "C" int hm_pick_filter_bits(int64_t n)
 { /* 45..90 filter bits per entry: measured optimum at 2e8 entries is 43..86 (7.6-8.0 ms), 21 costs
@@ -346,10 +358,16 @@ extern "C" int hm_k_build_filter(const uint64_t *d_keys, int64_t n, int filter_b
                         HM_FILTER_MIN_BITS,HM_FILTER_MAX_BITS);
   HM_CUDA(cudaMemsetAsync(d_filter,0,sizeof(uint32_t)*(size_t) hm_filter_words(filter_bits),
                           (cudaStream_t) stream));
-  if (n <= 0)
+  return hm_build_filter_range(d_keys,filter_bits,d_filter,0,n,stream);
+}
+
+/* set the bits of entries [i0,i1) (entries [0,i1) in place, filter zeroed by the caller) */
+int hm_build_filter_range(const uint64_t *d_keys, int filter_bits, uint32_t *d_filter,
+                          int64_t i0, int64_t i1, void *stream)
+{ if (i1 <= i0)
     return HM_OK;
-  int64_t nblk = (n+255)/256;
-  filter_build_kernel<<<(unsigned) nblk,256,0,(cudaStream_t) stream>>>(d_keys,n,64-filter_bits,d_filter);
+  int64_t nblk = (i1-i0+255)/256;
+  filter_build_kernel<<<(unsigned) nblk,256,0,(cudaStream_t) stream>>>(d_keys,i0,i1,64-filter_bits,d_filter);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return hm_cuda_fail(e,"filter_build_kernel");

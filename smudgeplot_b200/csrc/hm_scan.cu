@@ -69,16 +69,59 @@ int hm_peer_sum_plot(unsigned long long **plot, const int *dev, cudaStream_t *st
 int hm_condition_arrays(int kmer, int ethresh, int do_trim, int do_symm,
                         uint64_t **pk, uint64_t **pl, uint16_t **pc, int64_t *pn, cudaStream_t st);
 
+/* Device allocations of a one-GPU scan come from the device's stream-ordered memory pool with a
+ * release threshold of "never": a second hm_scan_create in the same process (bench e2e leg, a
+ * service handling many tables) reuses the memory instead of paying cudaMalloc / cudaFree of
+ * several GB every call (measured: ~20 ms of a 61 ms call).  Multi-GPU scans keep cudaMalloc:
+ * their arrays are mapped by the peers.  HETMERS_NO_POOL=1 disables the pool.                  */
+#define POOL_MAX 32
+typedef struct { void *p[POOL_MAX]; int n, enabled; } PoolReg;
+static PoolReg g_pool[64];
+
+static void pool_setup(int dev, int enable)
+{ static int configured[64] = {0};
+  if (dev < 0 || dev >= 64) return;
+  g_pool[dev].enabled = enable && getenv("HETMERS_NO_POOL") == NULL;
+  if (g_pool[dev].enabled && !configured[dev])
+    { cudaMemPool_t pool;
+      unsigned long long never = ~0ull;
+      if (cudaDeviceGetDefaultMemPool(&pool,dev) != cudaSuccess ||
+          cudaMemPoolSetAttribute(pool,cudaMemPoolAttrReleaseThreshold,&never) != cudaSuccess)
+        { cudaGetLastError(); g_pool[dev].enabled = 0; }
+      configured[dev] = 1;
+    }
+}
+
+static cudaError_t dalloc(int dev, cudaStream_t st, void **p, size_t bytes)
+{ PoolReg *R = (dev >= 0 && dev < 64) ? g_pool+dev : NULL;
+  if (R != NULL && R->enabled && R->n < POOL_MAX)
+    { cudaError_t e = cudaMallocAsync(p,bytes,st);
+      if (e == cudaSuccess)
+        { R->p[R->n++] = *p; return e; }
+      cudaGetLastError();
+    }
+  return cudaMalloc(p,bytes);
+}
+
+static void dfree(int dev, cudaStream_t st, void *p)
+{ PoolReg *R = (dev >= 0 && dev < 64) ? g_pool+dev : NULL;
+  if (p == NULL) return;
+  if (R != NULL)
+    for (int k = 0; k < R->n; k++)
+      if (R->p[k] == p)
+        { R->p[k] = R->p[--R->n];
+          cudaFreeAsync(p,st);
+          return;
+        }
+  cudaFree(p);
+}
+
 static void free_dev(DevTable *D)
 { cudaSetDevice(D->dev);
-  if (D->keys)   cudaFree(D->keys);
-  if (D->keys_lo) cudaFree(D->keys_lo);
-  if (D->cnt)    cudaFree(D->cnt);
-  if (D->deg)    cudaFree(D->deg);
-  if (D->bucket) cudaFree(D->bucket);
-  if (D->filter) cudaFree(D->filter);
-  if (D->up)     cudaFree(D->up);
-  if (D->plot)   cudaFree(D->plot);
+  dfree(D->dev,D->st,D->keys);  dfree(D->dev,D->st,D->keys_lo); dfree(D->dev,D->st,D->cnt);
+  dfree(D->dev,D->st,D->deg);   dfree(D->dev,D->st,D->bucket);  dfree(D->dev,D->st,D->filter);
+  dfree(D->dev,D->st,D->up);    dfree(D->dev,D->st,D->plot);
+  if (D->st) cudaStreamSynchronize(D->st);
   if (D->st)      cudaStreamDestroy(D->st);
   if (D->st_copy) cudaStreamDestroy(D->st_copy);
   memset(D,0,sizeof(*D));
@@ -181,12 +224,18 @@ static int load_range(hm_scan *s, DevTable *D, const hm_host_table *t, const int
     chunk = LOAD_CHUNK/2;
   if (chunk > count) chunk = count;
   for (int i = 0; i < 2; i++)
-    { HM_CUDA(cudaMalloc(&stage[i],(size_t) chunk*pbyte));
+    { HM_CUDA(dalloc(D->dev,D->st,(void **) &stage[i],(size_t) chunk*pbyte));
       if (staged)
         HM_CUDA(cudaHostAlloc(&pin[i],(size_t) chunk*pbyte,cudaHostAllocDefault));
       HM_CUDA(cudaEventCreateWithFlags(&copied[i],cudaEventDisableTiming));
       HM_CUDA(cudaEventCreateWithFlags(&unpacked[i],cudaEventDisableTiming));
     }
+  /* one GPU: the whole table arrives here in order, so the bucket index and the prefix filter are
+   * built chunk by chunk right behind the unpack (hidden behind the next chunk's H2D)           */
+  const int inc = (s->ngpu == 1 && first == 0 && count == s->n);
+  if (inc)
+    HM_CUDA(cudaMemsetAsync(D->filter,0,sizeof(uint32_t)*(size_t) hm_filter_words(s->fpos),D->st));
+  HM_CUDA(cudaStreamSynchronize(D->st));         /* (pool) allocations are used on both streams */
   int64_t pstart = 0;                               /* ordinal of the part's first record */
   for (int p = 0; p < t->nparts && rc == HM_OK; p++)
     { int64_t pn   = t->part_nels[p];
@@ -214,6 +263,12 @@ static int load_range(hm_scan *s, DevTable *D, const hm_host_table *t, const int
                                    D->keys_lo ? D->keys_lo+o : NULL,D->cnt+o,D->st);
           s->launches += 1;
           cudaEventRecord(unpacked[b],D->st);
+          if (inc && rc == HM_OK)
+            { rc = hm_build_bucket_index_range(D->keys,s->n,s->bits,D->bucket,s->idx64,o,o+m,D->st);
+              if (rc == HM_OK)
+                rc = hm_build_filter_range(D->keys,s->fpos,D->filter,o,o+m,D->st);
+              s->launches += 2;
+            }
           used[b] = 1;
           b ^= 1;
         }
@@ -222,7 +277,7 @@ static int load_range(hm_scan *s, DevTable *D, const hm_host_table *t, const int
   cudaStreamSynchronize(D->st_copy);
   cudaError_t e = cudaStreamSynchronize(D->st);
   for (int i = 0; i < 2; i++)
-    { cudaFree(stage[i]); cudaEventDestroy(copied[i]); cudaEventDestroy(unpacked[i]);
+    { dfree(D->dev,D->st,stage[i]); cudaEventDestroy(copied[i]); cudaEventDestroy(unpacked[i]);
       if (pin[i] != NULL) cudaFreeHost(pin[i]);
     }
   if (rc == HM_OK && e != cudaSuccess)
@@ -266,17 +321,18 @@ extern "C" int hm_scan_create(const hm_host_table *t, const int *dev, int n_gpus
       cudaError_t e;
 #define TRY(call) if (rc == HM_OK && (e = (call)) != cudaSuccess) rc = hm_cuda_fail(e,#call)
       TRY(cudaSetDevice(D->dev));
+      pool_setup(D->dev,n_gpus == 1);
       TRY(cudaStreamCreateWithFlags(&D->st,cudaStreamNonBlocking));
       TRY(cudaStreamCreateWithFlags(&D->st_copy,cudaStreamNonBlocking));
-      TRY(cudaMalloc(&D->keys,sizeof(uint64_t)*(size_t) (n+1)));
+      TRY(dalloc(D->dev,D->st,(void **) &D->keys,sizeof(uint64_t)*(size_t) (n+1)));
       if (t->kmer > 32)
-        TRY(cudaMalloc(&D->keys_lo,sizeof(uint64_t)*(size_t) (n+1)));
-      TRY(cudaMalloc(&D->cnt,sizeof(uint16_t)*(size_t) (n+1)));
-      TRY(cudaMalloc(&D->deg,(size_t) ((n+4)&~3ll)));
-      TRY(cudaMalloc(&D->bucket,ib*(((size_t) 1<<s->bits)+1)));
-      TRY(cudaMalloc(&D->filter,sizeof(uint32_t)*(size_t) hm_filter_words(s->fpos)));
-      TRY(cudaMalloc(&D->up,ib*(size_t) (D->hi-D->lo+1)));
-      TRY(cudaMalloc(&D->plot,sizeof(unsigned long long)*HM_PLOT_CELLS));
+        TRY(dalloc(D->dev,D->st,(void **) &D->keys_lo,sizeof(uint64_t)*(size_t) (n+1)));
+      TRY(dalloc(D->dev,D->st,(void **) &D->cnt,sizeof(uint16_t)*(size_t) (n+1)));
+      TRY(dalloc(D->dev,D->st,(void **) &D->deg,(size_t) ((n+4)&~3ll)));
+      TRY(dalloc(D->dev,D->st,(void **) &D->bucket,ib*(((size_t) 1<<s->bits)+1)));
+      TRY(dalloc(D->dev,D->st,(void **) &D->filter,sizeof(uint32_t)*(size_t) hm_filter_words(s->fpos)));
+      TRY(dalloc(D->dev,D->st,(void **) &D->up,ib*(size_t) (D->hi-D->lo+1)));
+      TRY(dalloc(D->dev,D->st,(void **) &D->plot,sizeof(unsigned long long)*HM_PLOT_CELLS));
 #undef TRY
     }
 
@@ -287,12 +343,13 @@ extern "C" int hm_scan_create(const hm_host_table *t, const int *dev, int n_gpus
     { DevTable *D = s->d+g;
       int64_t  *d_index = NULL;
       cudaSetDevice(D->dev);
-      cudaError_t e = cudaMalloc(&d_index,sizeof(int64_t)*ixlen);
+      cudaError_t e = dalloc(D->dev,D->st,(void **) &d_index,sizeof(int64_t)*ixlen);
       if (e != cudaSuccess) { rc = hm_cuda_fail(e,"cudaMalloc(stub index)"); break; }
       e = cudaMemcpyAsync(d_index,t->index,sizeof(int64_t)*ixlen,cudaMemcpyHostToDevice,D->st);
-      if (e != cudaSuccess) { rc = hm_cuda_fail(e,"cudaMemcpyAsync(stub index)"); cudaFree(d_index); break; }
+      if (e != cudaSuccess) { rc = hm_cuda_fail(e,"cudaMemcpyAsync(stub index)"); dfree(D->dev,D->st,d_index); break; }
+      cudaStreamSynchronize(D->st);          /* pool memory is about to be used on the copy stream too */
       rc = load_range(s,D,t,d_index,D->lo,D->hi-D->lo);
-      cudaFree(d_index);
+      dfree(D->dev,D->st,d_index);
     }
   double t_rec = now_ms();
   if (n_gpus > 1 && rc == HM_OK)
@@ -316,7 +373,7 @@ extern "C" int hm_scan_create(const hm_host_table *t, const int *dev, int n_gpus
       for (int g = 0; g < n_gpus; g++)
         { cudaSetDevice(s->d[g].dev); cudaStreamSynchronize(s->d[g].st); }
     }
-  for (int g = 0; g < n_gpus && rc == HM_OK; g++)
+  for (int g = 0; g < n_gpus && rc == HM_OK && n_gpus > 1; g++)     /* (one GPU: done chunk-wise) */
     { DevTable *D = s->d+g;
       cudaSetDevice(D->dev);
       rc = hm_k_build_bucket_index(D->keys,n,s->bits,D->bucket,s->idx64,D->st);
@@ -353,10 +410,20 @@ extern "C" int hm_scan_condition(hm_scan *s, int ethresh, int do_trim, int do_sy
       int64_t   n = s->n;
       HM_CUDA(cudaSetDevice(D->dev));
       HM_CUDA(cudaStreamSynchronize(D->st));
-      if (D->deg)    { cudaFree(D->deg);    D->deg = NULL; }
-      if (D->up)     { cudaFree(D->up);     D->up = NULL; }
-      if (D->bucket) { cudaFree(D->bucket); D->bucket = NULL; }
-      if (D->filter) { cudaFree(D->filter); D->filter = NULL; }
+      dfree(D->dev,D->st,D->deg);    D->deg = NULL;
+      dfree(D->dev,D->st,D->up);     D->up = NULL;
+      dfree(D->dev,D->st,D->bucket); D->bucket = NULL;
+      dfree(D->dev,D->st,D->filter); D->filter = NULL;
+      /* the table arrays are about to be replaced by plain cudaMalloc'ed ones: hand pooled ones back */
+      { PoolReg *R = g_pool + (D->dev < 64 ? D->dev : 0);
+        void *arr[3] = { D->keys, D->keys_lo, D->cnt };
+        for (int a = 0; a < 3; a++)
+          for (int k = 0; k < R->n; k++)
+            if (arr[a] != NULL && R->p[k] == arr[a])
+              { /* conditioning frees these with cudaFree, which is legal for pool memory */
+                R->p[k] = R->p[--R->n];
+              }
+      }
       rc = hm_condition_arrays(s->kmer,ethresh,do_trim,do_symm,&D->keys,&D->keys_lo,&D->cnt,&n,D->st);
       s->launches += 6;
       if (rc != HM_OK) return rc;
@@ -378,10 +445,10 @@ extern "C" int hm_scan_condition(hm_scan *s, int ethresh, int do_trim, int do_sy
       D->hi = n*(g+1)/G;
 #define TRY(call) if (rc == HM_OK && (e = (call)) != cudaSuccess) rc = hm_cuda_fail(e,#call)
       TRY(cudaSetDevice(D->dev));
-      TRY(cudaMalloc(&D->deg,(size_t) ((n+4)&~3ll)));
-      TRY(cudaMalloc(&D->bucket,ib*(((size_t) 1<<s->bits)+1)));
-      TRY(cudaMalloc(&D->filter,sizeof(uint32_t)*(size_t) hm_filter_words(s->fpos)));
-      TRY(cudaMalloc(&D->up,ib*(size_t) (D->hi-D->lo+1)));
+      TRY(dalloc(D->dev,D->st,(void **) &D->deg,(size_t) ((n+4)&~3ll)));
+      TRY(dalloc(D->dev,D->st,(void **) &D->bucket,ib*(((size_t) 1<<s->bits)+1)));
+      TRY(dalloc(D->dev,D->st,(void **) &D->filter,sizeof(uint32_t)*(size_t) hm_filter_words(s->fpos)));
+      TRY(dalloc(D->dev,D->st,(void **) &D->up,ib*(size_t) (D->hi-D->lo+1)));
 #undef TRY
       if (rc == HM_OK)
         rc = hm_k_build_bucket_index(D->keys,n,s->bits,D->bucket,s->idx64,D->st);
