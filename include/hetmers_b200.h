@@ -101,7 +101,11 @@ typedef struct hm_shards
     int32_t  self;                          /* the calling GPU's shard                          */
     int64_t  off[HM_MAX_SHARDS+1];
     uint8_t *deg[HM_MAX_SHARDS];
-  } hm_shards;
+    void    *scratch;                       /* optional device scratch for pass 2: look-ups of       */
+    int64_t  scratch_bytes;                 /*   foreign partners are batched instead of done inline */
+  } hm_shards;                              /*   (size: hm_pass2_scratch_bytes)                      */
+
+int64_t hm_pass2_scratch_bytes(int64_t range, int idx64);
 
 /* Pass 1 (PASS1=1 of PloidyPlot.c:1489; analysis_in_core_1 :454-568, analysis_thread_1
  * :168-301, big_window :712-842): for every entry x in [lo,hi) find every one-substitution

@@ -18,7 +18,7 @@ PLOT_CELLS = (SMAX + 1) * (FMAX + 1)
 ABI_SYMBOLS = [
     "hm_last_error", "hm_abi_version", "hm_device_count", "hm_device_info",
     "hm_k_unpack_records", "hm_k_build_bucket_index", "hm_k_pass1_degree", "hm_k_pass2_plot",
-    "hm_k_min_count", "hm_k_find_keys", "hm_pick_bucket_bits", "hm_k_pass2_extract", "hm_scan_extract",
+    "hm_k_min_count", "hm_k_find_keys", "hm_pick_bucket_bits", "hm_k_pass2_extract", "hm_scan_extract", "hm_pass2_scratch_bytes",
     "hm_k_build_filter", "hm_filter_words", "hm_pick_filter_bits",
     "hm_dev_alloc", "hm_dev_free", "hm_ipc_export", "hm_ipc_open", "hm_ipc_close", "hm_p2p_native_atomics",
     "hm_scan_create", "hm_set_io_threads", "hm_scan_destroy", "hm_scan_examine", "hm_scan_condition", "hm_scan_run", "hm_hetmers_host",
@@ -39,7 +39,7 @@ MAX_SHARDS = 16
 class Shards(C.Structure):
     """hm_shards: shard offsets + every owner's full-length incidence array as seen from this GPU"""
     _fields_ = [("n_shards", C.c_int32), ("self_", C.c_int32), ("off", C.c_int64 * (MAX_SHARDS + 1)),
-                ("deg", C.c_void_p * MAX_SHARDS)]
+                ("deg", C.c_void_p * MAX_SHARDS), ("scratch", C.c_void_p), ("scratch_bytes", C.c_int64)]
 
 
 class PairRec(C.Structure):
@@ -97,6 +97,8 @@ def lib():
     L.hm_k_min_count.argtypes = [vp, i64, i64, vp, vp]
     L.hm_k_find_keys.argtypes = [vp, vp, i64, vp, i32, i32, vp, vp, i64, vp, vp]
     L.hm_pick_bucket_bits.argtypes = [i64]
+    L.hm_pass2_scratch_bytes.argtypes = [i64, i32]
+    L.hm_pass2_scratch_bytes.restype = i64
     L.hm_scan_create.argtypes = [C.POINTER(HostTable), C.POINTER(i32), i32, C.POINTER(vp)]
     L.hm_scan_destroy.argtypes = [vp]
     L.hm_scan_destroy.restype = None

@@ -395,6 +395,9 @@ struct DegView
     int       n;                               /* shards (0 = everything is local)               */
     int64_t   off[HM_MAX_SHARDS+1];
     uint32_t *peer[HM_MAX_SHARDS];
+    uint32_t *defer_cnt;                       /* pass 2: per-CTA counts of deferred foreign look-ups */
+    void     *defer_ent;                       /*         their (entry, partner) index pairs          */
+    int64_t   defer_cap;                       /*         entries per CTA (0 = look up inline)        */
   };
 
 static DegView make_deg_view(uint8_t *d_deg, int64_t lo, int64_t hi, const hm_shards *sh)
@@ -410,6 +413,8 @@ static DegView make_deg_view(uint8_t *d_deg, int64_t lo, int64_t hi, const hm_sh
     }
   return v;
 }
+
+#define P2_DEFER_HEADER 4096                   /* bytes reserved for the per-CTA counters */
 
 __device__ __forceinline__ uint32_t *deg_words(const DegView &v, int64_t j)
 { if (j >= v.lo && j < v.hi)
@@ -739,9 +744,13 @@ pass2_plot_kernel(const uint16_t *__restrict__ cnt, const DegView dv,
                   const IdxT *__restrict__ up, int64_t lo, int64_t hi,
                   unsigned long long *__restrict__ plot)
 { extern __shared__ uint32_t tile[];
+  __shared__ unsigned s_defer;
   for (int t = threadIdx.x; t < P2_TS*P2_TM; t += blockDim.x)
     tile[t] = 0;
+  if (threadIdx.x == 0)
+    s_defer = 0;
   __syncthreads();
+  IdxT *const defer = (IdxT *) dv.defer_ent + 2*dv.defer_cap*blockIdx.x;
   /* P2_ILP entries per thread and trip: all their independent loads (degree bytes, partner
    * indices, then both partner look-ups at once) are in flight together -- the kernel is bound by
    * the latency of the two dependent gathers, not by bytes or instructions                      */
@@ -764,7 +773,17 @@ pass2_plot_kernel(const uint16_t *__restrict__ cnt, const DegView dv,
         { dj[u] = 2; ci[u] = cj[u] = 0;
           if (j[u] != IdxNone<IdxT>::value)
             { const uint8_t *pj = (const uint8_t *) deg_words(dv,(int64_t) j[u]);
-              dj[u] = (pj == (const uint8_t *) dv.self) ? __ldg(pj+j[u]) : __ldcv(pj+j[u]);  /* foreign: peer load */
+              if (pj != (const uint8_t *) dv.self)
+                { /* partner owned by another GPU: a ~2 us NVLink round trip.  Park the pair in this
+                   * CTA's slice of the defer list; pass2_deferred_kernel resolves all of them with
+                   * every remote load in flight at once (inline only when the slice is full)      */
+                  unsigned at = dv.defer_cap > 0 ? atomicAdd(&s_defer,1u) : 0xffffffffu;
+                  if ((int64_t) at < dv.defer_cap)
+                    { defer[2*at] = (IdxT) (i0 + (int64_t) u * blockDim.x); defer[2*at+1] = j[u]; continue; }
+                  dj[u] = __ldcv(pj+j[u]);
+                }
+              else
+                dj[u] = __ldg(pj+j[u]);
               cj[u] = __ldg(cnt+j[u]);
               ci[u] = cnt[i0 + (int64_t) u * blockDim.x];
             }
@@ -781,11 +800,37 @@ pass2_plot_kernel(const uint16_t *__restrict__ cnt, const DegView dv,
           }
     }
   __syncthreads();
+  if (threadIdx.x == 0 && dv.defer_cap > 0)
+    dv.defer_cnt[blockIdx.x] = (s_defer < (unsigned) dv.defer_cap) ? s_defer : (unsigned) dv.defer_cap;
   for (int t = threadIdx.x; t < P2_TS*P2_TM; t += blockDim.x)
     { uint32_t v = tile[t];
       if (v != 0)
         atomicAdd(plot + (t/P2_TM)*HM_PLOT_W + (t%P2_TM), (unsigned long long) v);
     }
+}
+
+/* the pairs pass2_plot_kernel parked: partner's incidence byte lives on another GPU */
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+pass2_deferred_kernel(const uint16_t *__restrict__ cnt, const DegView dv,
+                      unsigned long long *__restrict__ plot)
+{ const unsigned nb = dv.defer_cnt[blockIdx.x];
+  const IdxT *defer = (const IdxT *) dv.defer_ent + 2*dv.defer_cap*blockIdx.x;
+  for (unsigned e = threadIdx.x; e < nb; e += blockDim.x)
+    { int64_t i = (int64_t) defer[2*e], j = (int64_t) defer[2*e+1];
+      const uint8_t *pj = (const uint8_t *) deg_words(dv,j);
+      if (__ldcv(pj+j) > 1)
+        continue;
+      int ci = cnt[i], cj = __ldg(cnt+j);
+      int s  = ci+cj;
+      int m  = ci < cj ? ci : cj;
+      atomicAdd(plot + s*HM_PLOT_W + m, 1ull);
+    }
+}
+
+extern "C" int64_t hm_pass2_scratch_bytes(int64_t range, int idx64)
+{ int64_t cap = range/16 + 65536;            /* foreign partners are a few % of the isolated pairs */
+  return P2_DEFER_HEADER + cap * 2 * (idx64 ? 8 : 4);
 }
 
 extern "C" int hm_k_pass2_plot(const uint16_t *d_cnt, const uint8_t *d_deg, const void *d_up,
@@ -812,6 +857,13 @@ extern "C" int hm_k_pass2_plot(const uint16_t *d_cnt, const uint8_t *d_deg, cons
   int64_t want = (hi-lo+P2_THREADS*P2_ILP-1)/(P2_THREADS*P2_ILP);
   int     grid = (int) (want < sms*P2_CTAS_PER_SM ? want : sms*P2_CTAS_PER_SM);
   DegView dv   = make_deg_view((uint8_t *) d_deg,lo,hi,shards);
+  if (grid > P2_DEFER_HEADER/4) grid = P2_DEFER_HEADER/4;
+  if (dv.n > 1 && shards->scratch != NULL &&
+      shards->scratch_bytes >= P2_DEFER_HEADER + (int64_t) grid*2*(idx64 ? 8 : 4))
+    { dv.defer_cnt = (uint32_t *) shards->scratch;
+      dv.defer_ent = (uint8_t *) shards->scratch + P2_DEFER_HEADER;
+      dv.defer_cap = (shards->scratch_bytes-P2_DEFER_HEADER) / (2*(idx64 ? 8 : 4)) / grid;
+    }
   if (idx64)
     pass2_plot_kernel<uint64_t><<<grid,P2_THREADS,smem,(cudaStream_t) stream>>>
         (d_cnt,dv,(const uint64_t *) d_up,lo,hi,d_plot);
@@ -821,6 +873,13 @@ extern "C" int hm_k_pass2_plot(const uint16_t *d_cnt, const uint8_t *d_deg, cons
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return hm_cuda_fail(e,"pass2_plot_kernel");
+  if (dv.defer_cap > 0)
+    { if (idx64) pass2_deferred_kernel<uint64_t><<<grid,256,0,(cudaStream_t) stream>>>(d_cnt,dv,d_plot);
+      else       pass2_deferred_kernel<uint32_t><<<grid,256,0,(cudaStream_t) stream>>>(d_cnt,dv,d_plot);
+      e = cudaGetLastError();
+      if (e != cudaSuccess)
+        return hm_cuda_fail(e,"pass2_deferred_kernel");
+    }
   return HM_OK;
 }
 

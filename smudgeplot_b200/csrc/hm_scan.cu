@@ -40,6 +40,8 @@ typedef struct
     void               *bucket;
     uint32_t           *filter;       /* prefix presence bitmap */
     void               *up;           /* hi-lo entries */
+    void               *p2scratch;    /* pass 2 defer list (multi-GPU peer mode) */
+    int64_t             p2scratch_bytes;
     unsigned long long *plot;
     int64_t             lo, hi;       /* this device's work range */
   } DevTable;
@@ -121,6 +123,7 @@ static void free_dev(DevTable *D)
   dfree(D->dev,D->st,D->keys);  dfree(D->dev,D->st,D->keys_lo); dfree(D->dev,D->st,D->cnt);
   dfree(D->dev,D->st,D->deg);   dfree(D->dev,D->st,D->bucket);  dfree(D->dev,D->st,D->filter);
   dfree(D->dev,D->st,D->up);    dfree(D->dev,D->st,D->plot);
+  if (D->p2scratch) cudaFree(D->p2scratch);
   if (D->st) cudaStreamSynchronize(D->st);
   if (D->st)      cudaStreamDestroy(D->st);
   if (D->st_copy) cudaStreamDestroy(D->st_copy);
@@ -567,6 +570,15 @@ extern "C" int hm_scan_run(hm_scan *s, int64_t *plot, hm_scan_stats *stats)
         for (int r = 0; r < G; r++)
           { sh[g].off[r] = s->d[r].lo; sh[g].deg[r] = s->d[r].deg; }
         sh[g].off[G] = n;
+        DevTable *D = s->d+g;
+        int64_t need = hm_pass2_scratch_bytes(D->hi-D->lo,s->idx64);
+        if (D->p2scratch == NULL || D->p2scratch_bytes < need)
+          { HM_CUDA(cudaSetDevice(D->dev));
+            if (D->p2scratch) cudaFree(D->p2scratch);
+            HM_CUDA(cudaMalloc(&D->p2scratch,(size_t) need));
+            D->p2scratch_bytes = need;
+          }
+        sh[g].scratch = D->p2scratch; sh[g].scratch_bytes = D->p2scratch_bytes;
       }
 
   for (int g = 0; g < G; g++)

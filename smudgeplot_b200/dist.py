@@ -274,6 +274,11 @@ class ShardedScan:
         self._step += 1
         t.deg_ptr = self.peer.own + par * self.peer.nbytes
         t.shards = self.peer.shards(self.offsets, par)
+        if getattr(t, "_p2_scratch", None) is None:     # pass 2 batches its foreign look-ups through this
+            t._p2_scratch = torch.empty(t.L.hm_pass2_scratch_bytes(t.hi - t.lo, t.idx64), dtype=torch.uint8,
+                                        device=t.device)
+        t.shards.scratch = t._p2_scratch.data_ptr()
+        t.shards.scratch_bytes = t._p2_scratch.numel()
         ph = self._phase_events() if self.profile_phases else None
         t.plot.zero_()
         if events is not None:
