@@ -96,35 +96,46 @@ def allreduce_plot(plot: torch.Tensor, group=None):
     return plot
 
 
-def balanced_offsets(keys_full: torch.Tensor, world: int):
+def balanced_offsets(keys_full: torch.Tensor, world: int, depth: int = 3, per_candidate: float = 0.03):
     """Work ranges [off[r], off[r+1]) with equal pass-1 WORK rather than equal entry counts.
-    Only neighbours y > x are probed, so an entry whose first base is 'a' has three candidates at
-    position 0, 'c' two, 'g' one, 't' none -- about 3 of the ~22 filter probes per entry
-    (measured at 8 GPUs with equal counts: rank 0 9.8 ms, rank 7 8.3 ms).  Weight by first base."""
+    Only neighbours y > x are probed, so an entry with base b at position p has 3-b candidates
+    there ('a' three, 't' none) -- each ~3 % of an entry's cost.  For the first `depth` bases that
+    number is the same for whole stretches of the sorted table, so shards cut by count are
+    systematically uneven (measured at 8 GPUs: 9.8 vs 8.3 ms with equal counts; 9.4 vs 8.7 ms when
+    only the first base is weighted).  The table is split into the 4^depth prefix classes, each
+    weighted by its candidate count, and the cuts are placed on the cumulative weight."""
     n = keys_full.numel()
     if world <= 1:
         return [0, n]
     sign = -(1 << 63)
+    ncls = 4 ** depth
     flipped = keys_full ^ sign                                   # unsigned order as signed
-    marks = torch.tensor([(b << 62) ^ sign if b < 2 else ((b << 62) - (1 << 64)) ^ sign for b in (1, 2, 3)],
-                         dtype=torch.int64, device=keys_full.device)
-    bnd = [0] + [int(v) for v in torch.searchsorted(flipped, marks).tolist()] + [n]
-    w = [1.0 + 0.03 * (3 - b) for b in range(4)]                 # relative cost per entry by first base
-    total = sum(w[b] * (bnd[b + 1] - bnd[b]) for b in range(4))
-    offs, acc, b, pos = [0], 0.0, 0, 0
+    marks = []
+    for c in range(1, ncls):
+        v = c << (64 - 2 * depth)                                # first key of prefix class c (unsigned)
+        v = v - (1 << 64) if v >= (1 << 63) else v               # as the int64 bit pattern
+        marks.append(v ^ sign)
+    pos = torch.searchsorted(flipped, torch.tensor(marks, dtype=torch.int64, device=keys_full.device))
+    bnd = [0] + [int(v) for v in pos.tolist()] + [n]
+    w = []
+    for c in range(ncls):
+        cand = sum(3 - ((c >> (2 * (depth - 1 - p))) & 3) for p in range(depth))
+        w.append(1.0 + per_candidate * cand)
+    total = sum(w[c] * (bnd[c + 1] - bnd[c]) for c in range(ncls))
+    offs, acc, c, at = [0], 0.0, 0, 0
     for r in range(1, world):
         target = total * r / world
-        while b < 4 and acc + w[b] * (bnd[b + 1] - pos) < target:
-            acc += w[b] * (bnd[b + 1] - pos)
-            b += 1
-            pos = bnd[b] if b < 4 else n
-        if b >= 4:
+        while c < ncls and acc + w[c] * (bnd[c + 1] - at) < target:
+            acc += w[c] * (bnd[c + 1] - at)
+            c += 1
+            at = bnd[c] if c < ncls else n
+        if c >= ncls:
             offs.append(n)
             continue
-        step = int((target - acc) / w[b])
-        acc += w[b] * step
-        pos += step
-        offs.append(min(max(pos, offs[-1]), n))
+        step = int((target - acc) / w[c])
+        acc += w[c] * step
+        at += step
+        offs.append(min(max(at, offs[-1]), n))
     return offs + [n]
 
 

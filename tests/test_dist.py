@@ -78,3 +78,22 @@ def test_prefix_partition_tiles_the_prefix_space():
         parts = hd.prefix_partition(w)
         assert parts[0][0] == 0 and parts[-1][1] == 1 << 24
         assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+
+
+def test_balanced_offsets_are_a_monotone_cover_and_favour_heavy_prefixes():
+    sys.path.insert(0, ROOT)
+    from smudgeplot_b200 import dist as hd
+    from tools import synth
+    keys, _ = synth.synth_table(21, 60000, 2, 0.01, 40, 4, 3)
+    n = keys.numel()
+    for w in (1, 2, 3, 4, 8, 16):
+        o = hd.balanced_offsets(keys, w)
+        assert len(o) == w + 1 and o[0] == 0 and o[-1] == n
+        assert all(a <= b for a, b in zip(o, o[1:]))
+        sizes = [b - a for a, b in zip(o, o[1:])]
+        if w > 1:
+            assert max(sizes) < 1.25 * min(sizes)              # a mild correction, not a re-partition
+            assert sizes[0] < sizes[-1]                        # 'a...' entries cost more than 't...' ones
+    # degenerate inputs
+    assert hd.balanced_offsets(keys[:1], 4)[-1] == 1
+    assert hd.balanced_offsets(keys[:0], 2) == [0, 0, 0]
