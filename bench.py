@@ -332,6 +332,7 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline(args, dev)
         print(json.dumps(line), flush=True)
     if multi:
+        job.close()
         dist.barrier()
         dist.destroy_process_group()
 

@@ -198,6 +198,19 @@ class PeerDeg:
             return None
         return cls(own.value, peers, nbytes, rank)
 
+    def close(self, device):
+        """unmap the peers' arrays and free the own one (call on every rank, after a barrier)"""
+        import ctypes as C
+        from . import _lib
+        L = _lib.lib()
+        with torch.cuda.device(device):
+            for r, pp in enumerate(self.peers):
+                if pp is not None and r != self.rank:
+                    L.hm_ipc_close(C.c_void_p(pp))
+            if self.own:
+                L.hm_dev_free(C.c_void_p(self.own))
+        self.peers, self.own = [], None
+
     def shards(self, offsets, parity):
         """hm_shards over buffer `parity` (0/1) of every rank's allocation"""
         from . import _lib
@@ -254,6 +267,13 @@ class ShardedScan:
         kf, cf, lo, hi = gather_table(keys, cnt16, group)
         del keys, cnt16
         return cls(k, kf, cf, lo, hi, group)
+
+    def close(self):
+        if self.peer is not None:
+            torch.cuda.synchronize()
+            dist.barrier(self.group)              # nobody is still reading a peer's array
+            self.peer.close(self.table.device)
+            self.peer = None
 
     def scan(self, events=None):
         return self.scan_on(self.table, events)

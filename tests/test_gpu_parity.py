@@ -472,6 +472,14 @@ def test_multi_gpu_single_process_matches_single_gpu(ngpu, tmp_path):
     out = str(tmp_path / "o")
     hetmers.run_hetmers(name, o=out, L=12, t=4, gpus=ngpu)
     assert open(out + ".smu").read() == hetmers.smu_text(one)
+    # extract_kmer_pairs' pair list is the same set whichever GPU found the pair
+    pix = (one > 0).astype(np.uint16)
+    recs = []
+    for g in (1, ngpu):
+        with hetmers.Scan(kt, gpus=g) as sc:
+            sc.run()
+            recs.append(sc.extract(pix))
+    assert len(recs[0]) == int(one.sum()) and np.array_equal(recs[0], recs[1])
 
 
 def test_multi_gpu_dense_exchange_fallback(tmp_path, monkeypatch):
