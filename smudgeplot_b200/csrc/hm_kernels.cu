@@ -502,39 +502,45 @@ pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restric
        * ma holds positions [0,NA), mb positions [NA,PH).                                       */
       const uint32_t xh = (uint32_t) (x >> 32), xl = (uint32_t) x;
       uint32_t ma = 0, mb = 0;
+      /* the filter bit is  w >> (pf & 31)  with pf = the candidate's F-bit prefix.  Replacing base p
+       * leaves the low five prefix bits alone unless p is one of the last ~3 covered positions, so
+       * the shift that brings the bit to the TOP of the word (31 - (pf & 31)) is computed once per
+       * entry; a funnel shift then appends that top bit to the survivor mask in one instruction.  */
+      constexpr int LOWBITS = F <= 32 ? 37-F : 5-SFT;       /* bits of yh below the word index */
+      const uint32_t pf_own = F <= 32 ? (xh >> (32-F)) : ((xh << SFT) | (xl >> (32-SFT)));
+      const uint32_t sl_own = 31 - (pf_own & 31);
 #pragma unroll
       for (int p = 0; p < PH; p++)
         { const bool pa = (p <= pmax);
 #pragma unroll
           for (int c = 1; c <= 3; c++)
             { bool     act;
-              uint32_t widx, bit;
+              uint32_t widx, sl;
               if (p < 16)                                    /* base p lives in the high half */
                 { const int      s  = 30-2*p;
                   const uint32_t yh = (xh & ~(3u << s)) | ((uint32_t) c << s);
-                  act = pa && (yh > xh);
-                  if (F <= 32)
-                    { widx = yh >> (37-F);
-                      bit  = (yh >> (32-F)) & 31;
-                    }
+                  act  = pa && (yh > xh);
+                  widx = yh >> LOWBITS;
+                  if (s >= LOWBITS)                          /* low prefix bits untouched */
+                    sl = sl_own;
+                  else if (F <= 32)
+                    sl = 31 - ((yh >> (32-F)) & 31);
                   else
-                    { widx = yh >> (5-SFT);
-                      bit  = ((yh << SFT) | (xl >> (32-SFT))) & 31;
-                    }
+                    sl = 31 - (((yh << SFT) | (xl >> (32-SFT))) & 31);
                 }
               else                                           /* F > 32: base p in the low half */
                 { const int      s  = 62-2*p;
                   const uint32_t yl = (xl & ~(3u << s)) | ((uint32_t) c << s);
                   act  = pa && (yl > xl);
                   widx = xh >> (5-SFT);
-                  bit  = ((xh << SFT) | (yl >> (32-SFT))) & 31;
+                  sl   = 31 - (((xh << SFT) | (yl >> (32-SFT))) & 31);
                 }
               uint32_t w = 0;
               if (act)
                 w = __ldg(filter + widx);
-              const uint32_t hit = (w >> bit) & 1;
-              if (p < NA) ma = (ma << 1) | hit;
-              else        mb = (mb << 1) | hit;
+              const uint32_t top = w << sl;                  /* the filter bit, at bit 31 */
+              if (p < NA) ma = __funnelshift_l(top,ma,1);    /* (ma << 1) | bit */
+              else        mb = __funnelshift_l(top,mb,1);
             }
         }
 
