@@ -73,6 +73,36 @@ extern "C" int hm_pick_bucket_bits(int64_t n)
 
 template <typename IdxT> struct IdxNone { static constexpr IdxT value = (IdxT) ~(IdxT) 0; };
 
+/* Filter words are streamed (each probed column walks the bitmap once, no reuse), everything else
+ * pass 1 touches (keys, bucket offsets, counts) is re-read by neighbouring probes: ask L2 to drop
+ * the former first.  P1_FILTER_LD=0 plain __ldg, 1 L2::evict_first, 2 + L1::no_allocate.        */
+#ifndef P1_FILTER_LD
+#define P1_FILTER_LD 0
+#endif
+__device__ __forceinline__ uint64_t make_evict_first_policy(void)
+{ uint64_t pol = 0;
+#if P1_FILTER_LD >= 1
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#endif
+  return pol;
+}
+
+__device__ __forceinline__ uint32_t ld_filter(const uint32_t *p, uint64_t pol)
+{
+#if P1_FILTER_LD == 1
+  uint32_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+#elif P1_FILTER_LD == 2
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+#else
+  (void) pol;
+  return __ldg(p);
+#endif
+}
+
 /* exact match of y inside its prefix bucket; -1 if absent.  KW = 64-bit words per key (k <= 32: 1,
  * k <= 64: 2, second word in the parallel array keys_lo); buckets are prefixes of the first word. */
 template <typename IdxT, int KW>
@@ -473,6 +503,7 @@ pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restric
   uint64_t *ql = s_ql[KW == 2 ? warp : 0];
   IdxT     *qi = s_qi[warp];
   int       qn = 0;                                      /* warp-uniform queue fill */
+  const uint64_t pol = make_evict_first_policy();
 
   const int64_t nchunks = (hi-lo+31) >> 5;
   for (int64_t c = (int64_t) blockIdx.x * P1_WARPS + warp; c < nchunks;
@@ -537,7 +568,7 @@ pass1_filter_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restric
                 }
               uint32_t w = 0;
               if (act)
-                w = __ldg(filter + widx);
+                w = ld_filter(filter + widx,pol);
               const uint32_t top = w << sl;                  /* the filter bit, at bit 31 */
               if (p < NA) ma = __funnelshift_l(top,ma,1);    /* (ma << 1) | bit */
               else        mb = __funnelshift_l(top,mb,1);
