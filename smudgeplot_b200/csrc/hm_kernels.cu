@@ -406,7 +406,15 @@ int hm_build_filter_range(const uint64_t *d_keys, int filter_bits, uint32_t *d_f
 
 /* -------------------------------------------------------------------------- pass 1 ------ */
 
+#ifndef P1_WARPS
 #define P1_WARPS   8            /* warps per CTA                                     */
+#endif
+#ifndef P1_GRID_PER_SM
+#define P1_GRID_PER_SM 8192      /* cap on CTAs per SM: in practice one CTA per 8 chunks, started in table
+                                  * order.  Few persistent CTAs striding over the table drift apart and lose
+                                  * the L2 reuse of filter sectors between neighbours: 6/SM 8.77 ms, 32/SM
+                                  * 7.65, 96/SM 7.12, 1024/SM 6.78 (2e8 entries)                         */
+#endif
 #ifndef P1_MINBLOCKS
 #define P1_MINBLOCKS 6          /* resident CTAs per SM the register budget must allow (40 regs, no spills) */
 #endif
@@ -703,7 +711,7 @@ static cudaError_t launch_pass1(const uint64_t *keys, const uint64_t *keys_lo, c
   cudaDeviceGetAttribute(&sms,cudaDevAttrMultiProcessorCount,dev);
   int64_t nchunks = (hi-lo+31)>>5;
   int64_t want    = (nchunks+P1_WARPS-1)/P1_WARPS;
-  int64_t cap     = (int64_t) sms*8*4;            /* 4 waves of 8 resident CTAs per SM */
+  int64_t cap     = (int64_t) sms*P1_GRID_PER_SM;
   int     grid    = (int) (want < cap ? want : cap);
   pass1_filter_kernel<IdxT,F,KW><<<grid,P1_WARPS*32,0,st>>>
       (keys,keys_lo,cnt,n,(const IdxT *) bucket,64-bits,filter,kmer,lo,hi,dv,(IdxT *) up);
