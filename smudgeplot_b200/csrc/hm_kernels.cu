@@ -410,10 +410,11 @@ int hm_build_filter_range(const uint64_t *d_keys, int filter_bits, uint32_t *d_f
 #define P1_WARPS   8            /* warps per CTA                                     */
 #endif
 #ifndef P1_GRID_PER_SM
-#define P1_GRID_PER_SM 8192      /* cap on CTAs per SM: in practice one CTA per 8 chunks, started in table
-                                  * order.  Few persistent CTAs striding over the table drift apart and lose
-                                  * the L2 reuse of filter sectors between neighbours: 6/SM 8.77 ms, 32/SM
-                                  * 7.65, 96/SM 7.12, 1024/SM 6.78 (2e8 entries)                         */
+#define P1_GRID_PER_SM 1024      /* CTAs launched per SM, started in table order, each striding over a few
+                                  * groups of 8 chunks.  Few persistent CTAs drift apart and lose the L2
+                                  * reuse of filter sectors between neighbours: 6/SM 8.77 ms, 32/SM 7.65,
+                                  * 96/SM 7.12, 256/SM 6.87, 1024/SM 6.78; one CTA per 8 chunks (no stride)
+                                  * is slower again (~7.3 ms) (2e8 entries)                              */
 #endif
 #ifndef P1_MINBLOCKS
 #define P1_MINBLOCKS 6          /* resident CTAs per SM the register budget must allow (40 regs, no spills) */
