@@ -540,3 +540,25 @@ def test_one_process_per_gpu_nccl_matches_single_gpu(dense):
         assert ("NCCL" in exchange) == dense, exchange
         for p in plots:
             assert np.array_equal(p.reshape(-1), want)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_dense_asymmetric_tables_match_oracle(seed, tmp_path):
+    """arbitrary tables (not genome-like, NOT symmetric, tiny k, counts around the SMAX/FMAX gates):
+    nothing in the CUDA path may rely on strand symmetry or on sparse neighbourhoods"""
+    rng = np.random.default_rng(2000 + seed)
+    k = int(rng.integers(2, 10))
+    n = int(min(rng.integers(2, 3000), 4 ** k))
+    cmax = int(rng.choice([6, 40, 520, 700]))
+    vals = np.sort(rng.choice(4 ** k, size=n, replace=False).astype(np.uint64))
+    keys = vals << np.uint64(64 - 2 * k)
+    cnt = rng.integers(1, cmax + 1, size=n).astype(np.uint16)
+    ibyte = 1 if k < 8 else int(rng.integers(1, 3))
+    kt = fastk.write_ktab(str(tmp_path / "t"), k, keys, cnt, ibyte=ibyte, nparts=int(rng.integers(1, 4)))
+    want_plot, want_deg = ou.oracle_scan(fastk.keys_u64_to_bytes(keys, k), cnt, k)
+    with hetmers.Scan(kt) as sc:
+        plot, _ = sc.run()
+        got_keys, got_cnt, deg = sc.download()
+    assert np.array_equal(got_keys, keys) and np.array_equal(got_cnt, cnt)
+    assert np.array_equal(deg, want_deg)
+    assert np.array_equal(plot, want_plot)

@@ -161,3 +161,40 @@ def test_synth_table_is_trimmed_symmetric_and_deterministic():
     lo = synth.synth_table(21, 3000, 3, 0.02, 60, 12, 7, key_range=(0, 1 << 23))
     hi = synth.synth_table(21, 3000, 3, 0.02, 60, 12, 7, key_range=(1 << 23, 1 << 24))
     assert np.array_equal(np.concatenate([synth.keys_to_u64_numpy(lo[0]), synth.keys_to_u64_numpy(hi[0])]), ku)
+
+
+# ------------------------------------------------------------------ randomised small tables ----
+
+def _random_table(rng, k, n, cmax):
+    space = 4 ** k
+    n = min(n, space)
+    vals = np.sort(rng.choice(space, size=n, replace=False).astype(np.uint64))
+    keys = vals << np.uint64(64 - 2 * k)
+    cnt = rng.integers(1, cmax + 1, size=n).astype(np.uint16)
+    return keys, cnt
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_oracle_equals_brute_force_on_random_dense_tables(seed):
+    """arbitrary (not genome-like, not symmetric) tables: dense neighbourhoods, counts around the
+    SMAX = 1000 / FMAX = 500 gates, tiny k -- the oracle's trie/merge restatement against the
+    ten-line definition of SURVEY.md Appendix B"""
+    rng = np.random.default_rng(1000 + seed)
+    k = int(rng.integers(1, 9))
+    n = int(rng.integers(2, 600))
+    cmax = int(rng.choice([6, 40, 520, 700]))
+    keys, cnt = _random_table(rng, k, n, cmax)
+    plot_o, deg_o = ou.oracle_scan(fastk.keys_u64_to_bytes(keys, k), cnt, k)
+    plot_b, deg_b = ou.brute_force(keys, cnt, k)
+    assert np.array_equal(deg_o, deg_b)
+    assert np.array_equal(plot_o, plot_b)
+    # and the range-restricted kernel contracts (multi-GPU host-logic tests) compose to the same plot
+    cuts = sorted({0, len(keys)} | set(int(v) for v in rng.integers(0, len(keys) + 1, size=2)))
+    deg = np.zeros(len(keys), dtype=np.uint8)
+    ups = []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        d, up = ou.partial_pass1(keys, cnt, k, lo, hi)
+        deg += d
+        ups.append((lo, hi, up))
+    plot = sum(ou.partial_pass2(cnt, deg, up, lo, hi) for lo, hi, up in ups)
+    assert np.array_equal(deg, deg_b) and np.array_equal(plot, plot_b)
