@@ -33,8 +33,18 @@ sys.path.insert(0, ROOT)
 
 K, PLOIDY, HET, COV, LCUT, SEED = 31, 2, 0.01, 40.0, 12, 2
 ALGO_BYTES_PER_KMER = 2 * ((K + 3) // 4 + 2) + 2          # 22 B at k=31
-METRIC = "k-mers/sec scanned (hetmers)"
 UNIT = "k-mers/s"
+
+
+def _baseline_metric():
+    """the metric string of BASELINE.json (the driver compares against it), else a local default"""
+    try:
+        return json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
+    except Exception:
+        return "k-mers/sec scanned (hetmers)"
+
+
+METRIC = _baseline_metric()
 
 
 def parse():
