@@ -126,3 +126,84 @@ def test_no_gpu_means_loud_failure(built, tmp_path):
     from smudgeplot_b200 import fastk
     with pytest.raises(_lib.HetmersError):
         hetmers.scan_table(fastk.read_ktab(os.path.join(GOLDEN, "dip_k21", "dip_k21")))
+
+
+# ---------------------------------------------------------------- layer C on the CPU (plain C) ----
+
+def _open_table(path):
+    import ctypes as C
+    L = _lib.lib()
+    h = C.c_void_p()
+    rc = L.hm_table_open(path.encode(), C.byref(h))
+    return rc, h
+
+
+def test_layer_c_parser_matches_python_reader_on_goldens(built):
+    """hm_table_open (host/fastk_table.c) against smudgeplot_b200.fastk.read_ktab on every golden
+    table: header fields, part sizes, prefix index and the mapped payload bytes"""
+    import ctypes as C
+    import numpy as np
+    from conftest import golden_cases
+    from smudgeplot_b200 import fastk
+    L = _lib.lib()
+    for name in golden_cases():
+        path = os.path.join(GOLDEN, name, name)
+        kt = fastk.read_ktab(path)
+        rc, h = _open_table(path + ".ktab")                    # suffix accepted, like the reference
+        assert rc == 0, L.hm_last_error()
+        v = L.hm_table_view(h).contents
+        assert (v.kmer, v.ibyte, v.nparts, v.nels) == (kt.kmer, kt.ibyte, kt.nparts, kt.nels)
+        idx = np.ctypeslib.as_array(v.index, shape=(1 << (8 * kt.ibyte),))
+        assert np.array_equal(idx, kt.index)
+        for p in range(kt.nparts):
+            assert v.part_nels[p] == kt.part_nels[p]
+            nbytes = kt.part_nels[p] * kt.pbyte
+            if nbytes:
+                raw = (C.c_uint8 * nbytes).from_address(v.part_rec[p])
+                assert bytes(raw) == kt.records[p].tobytes()
+            assert v.part_fd[p] >= 0 and v.part_fd_off[p] == 12      # kept open for the pread loader
+        L.hm_table_close(h)
+
+
+def test_layer_c_error_codes(built, tmp_path):
+    import shutil
+    L = _lib.lib()
+    rc, _ = _open_table(str(tmp_path / "absent"))
+    assert rc == -4 and L.hm_last_error().decode().startswith("Cannot open k-mer table")      # HM_EIO
+    d = tmp_path / "g"
+    shutil.copytree(os.path.join(GOLDEN, "trip_k31"), d)
+    part = d / ".trip_k31.ktab.2"
+    data = part.read_bytes()
+    part.write_bytes(data[: len(data) // 2])                       # truncated payload
+    rc, _ = _open_table(str(d / "trip_k31"))
+    assert rc == -5 and "truncated" in L.hm_last_error().decode()  # HM_EFORMAT (the reference reads garbage)
+    part.write_bytes(b"\x15\x00\x00\x00" + data[4:])               # part says k=21, stub says k=31
+    rc, _ = _open_table(str(d / "trip_k31"))
+    assert rc == -5 and "k-mer length matching stub" in L.hm_last_error().decode()
+    stub = d / "trip_k31.ktab"
+    sb = stub.read_bytes()
+    stub.write_bytes(sb[:100])                                     # truncated prefix index
+    rc, _ = _open_table(str(d / "trip_k31"))
+    assert rc == -5 and "truncated prefix index" in L.hm_last_error().decode()
+    stub.write_bytes(sb[:12] + b"\x07\x00\x00\x00" + sb[16:])      # ibyte = 7
+    rc, _ = _open_table(str(d / "trip_k31"))
+    assert rc == -5 and "implausible stub header" in L.hm_last_error().decode()
+
+
+def test_layer_c_smu_writer_matches_oracle_writer(built, tmp_path):
+    import ctypes as C
+    import numpy as np
+    import oracle_util as ou
+    rng = np.random.default_rng(5)
+    plot = np.zeros((_lib.SMAX + 1, _lib.PLOT_W), dtype=np.int64)
+    s = rng.integers(0, _lib.SMAX + 1, size=4000)
+    m = np.minimum(rng.integers(0, _lib.PLOT_W, size=4000), s // 2)
+    np.add.at(plot, (s, m), rng.integers(1, 10**12, size=4000))
+    plot[1000, 500] = 7                                            # computed but never written (i < FMAX)
+    out = str(tmp_path / "w.smu")
+    assert _lib.lib().hm_write_smu(out.encode(), plot.ctypes.data) == 0
+    text = open(out).read()
+    assert text == ou.smu_text(plot) == hetmers.smu_text(plot)
+    assert "500\t500\t" not in text
+    rows = [tuple(int(v) for v in ln.split("\t")) for ln in text.splitlines()]
+    assert rows == sorted(rows, key=lambda r: (r[0] + r[1], r[0]))   # sum-major, then min (PloidyPlot.c:1612)
