@@ -73,6 +73,79 @@ static void die_hm(void)
   exit (1);
 }
 
+#ifdef EXTRACT_PAIRS
+
+/* The smudges named in the .sma file, in order of first appearance; label s+1 in the pixel map
+ * refers to set->v[s] (the reference keeps the same numbering in its PLOT array,
+ * PloidyList.c:1313-1350).                                                                    */
+typedef struct { Smudge *v; int n, cap; } SmudgeSet;
+
+static int smudge_label(SmudgeSet *set, int a, int b, const char *out_root)
+{ int s;
+  for (s = 0; s < set->n; s++)
+    if (set->v[s].a == a && set->v[s].b == b)
+      return (s+1);
+  if (set->n == set->cap)
+    { set->cap += 100;
+      set->v = realloc(set->v,set->cap*sizeof(Smudge));
+      if (set->v == NULL)
+        exit (1);
+    }
+  { char *name = malloc(strlen(out_root)+64);
+    sprintf(name,"%s.%dA%dB.txt",out_root,a,b);
+    set->v[s].a = a;
+    set->v[s].b = b;
+    set->v[s].f = fopen(name,"w");                  /* created even if no pair ends up in it */
+    free(name);
+  }
+  if (set->v[s].f == NULL)
+    { fprintf(stderr,"%s: Cannot open smudge file %s.%dA%dB.txt\n",Prog_Name,out_root,a,b);
+      exit (1);
+    }
+  set->n += 1;
+  return (s+1);
+}
+
+/* <arg>[.sma]: a header line, then "covB covA freq <a>A<b>B" per annotated pixel (written by
+ * `smudgeplot all`, cli.py:451-456).  Same acceptance rules and messages as PloidyList.c:1300-1335. */
+static void read_sma(const char *arg, const char *out_root, uint16_t *pixmap, SmudgeSet *set)
+{ size_t n = strlen(arg);
+  char  *root = strdup(arg), *name, line[1000];
+  FILE  *f;
+  int    covb, cova, a, b;
+
+  if (n > 4 && strcasecmp(root+n-4,".sma") == 0)
+    root[n-4] = '\0';
+  name = malloc(strlen(root)+8);
+  sprintf(name,"%s.sma",root);
+  f = fopen(name,"r");
+  if (f == NULL)
+    { fprintf(stderr,"\n%s: Could not open smudge file %s.sma",Prog_Name,root);
+      exit (1);
+    }
+  if (fgets(line,sizeof(line),f) != NULL)              /* the header is skipped unseen */
+    while (fgets(line,sizeof(line),f) != NULL)
+      { if (sscanf(line," %d %d %*d %dA%dB",&covb,&cova,&a,&b) != 4)
+          { fprintf(stderr,"%s: Cannot parse line '%s'\n",Prog_Name,line);
+            exit (1);
+          }
+        if (a <= 0 || b <= 0 || a < b)
+          { fprintf(stderr,"%s: %dA%dB is not a valid smudge label'\n",Prog_Name,a,b);
+            exit (1);
+          }
+        if (covb < 0 || covb > HM_FMAX || cova < covb || covb+cova > HM_SMAX)
+          { fprintf(stderr,"%s: (%d,%d) is not a valid pixel coordinate\n",Prog_Name,covb,cova);
+            exit (1);
+          }
+        pixmap[(covb+cova)*HM_PLOT_W+covb] = (uint16_t) smudge_label(set,a,b,out_root);
+      }
+  fclose(f);
+  free(name);
+  free(root);
+}
+
+#endif
+
 static int pick_gpus(int *devs)
 { int ngpu = 1, navail = hm_device_count(), i;
   const char *g = getenv("HETMERS_GPUS");
@@ -174,70 +247,13 @@ int main(int argc, char *argv[])
     }
 
 #ifdef EXTRACT_PAIRS
-  //  Read in the .sma file: pixel -> smudge map and one output file per smudge (PloidyList.c:1288-1352)
+  //  The annotated smudge file: pixel -> label map and one output file per label
 
   uint16_t *PIXMAP = calloc(HM_PLOT_CELLS,sizeof(uint16_t));
-  Smudge   *SMUDGE;
-  int       SM_NUM = 0;
-  { char *SMA = strdup(argv[2]);
-    size_t n = strlen(SMA);
-    char  *name, buf[1000];
-    FILE  *f;
-    int    pi, pj, a, b, sidx, nmax = 100;
-
-    if (n > 4 && strcasecmp(SMA+n-4,".sma") == 0)          /* PathnRoot(argv[2],".sma") */
-      SMA[n-4] = '\0';
-    name = malloc(strlen(SMA)+strlen(OUT)+64);
-    sprintf(name,"%s.sma",SMA);
-    f = fopen(name,"r");
-    if (f == NULL)
-      { fprintf(stderr,"\n%s: Could not open smudge file %s.sma",Prog_Name,SMA);
-        exit (1);
-      }
-    SMUDGE = malloc(nmax*sizeof(Smudge));
-    if (PIXMAP == NULL || SMUDGE == NULL)
-      exit (1);
-    if (fgets(buf,1000,f) == NULL)                           /* header line */
-      buf[0] = '\0';
-    while (fgets(buf,1000,f) != NULL)
-      { if (sscanf(buf," %d %d %*d %dA%dB",&pi,&pj,&a,&b) != 4)
-          { fprintf(stderr,"%s: Cannot parse line '%s'\n",Prog_Name,buf);
-            exit (1);
-          }
-        if (a <= 0 || b <= 0 || a < b)
-          { fprintf(stderr,"%s: %dA%dB is not a valid smudge label'\n",Prog_Name,a,b);
-            exit (1);
-          }
-        if (pi < 0 || pi > HM_FMAX || pj < pi || pi+pj > HM_SMAX)
-          { fprintf(stderr,"%s: (%d,%d) is not a valid pixel coordinate\n",Prog_Name,pi,pj);
-            exit (1);
-          }
-        for (sidx = 0; sidx < SM_NUM; sidx++)
-          if (SMUDGE[sidx].a == a && SMUDGE[sidx].b == b)
-            break;
-        if (sidx >= SM_NUM)
-          { if (SM_NUM >= nmax)
-              { nmax += 100;
-                SMUDGE = realloc(SMUDGE,nmax*sizeof(Smudge));
-                if (SMUDGE == NULL)
-                  exit (1);
-              }
-            SMUDGE[sidx].a = a;
-            SMUDGE[sidx].b = b;
-            sprintf(name,"%s.%dA%dB.txt",OUT,a,b);
-            SMUDGE[sidx].f = fopen(name,"w");
-            if (SMUDGE[sidx].f == NULL)
-              { fprintf(stderr,"%s: Cannot open smudge file %s.%dA%dB.txt\n",Prog_Name,OUT,a,b);
-                exit (1);
-              }
-            SM_NUM += 1;
-          }
-        PIXMAP[(pi+pj)*HM_PLOT_W+pi] = (uint16_t) (sidx+1);
-      }
-    fclose(f);
-    free(name);
-    free(SMA);
-  }
+  SmudgeSet SM = { NULL, 0, 0 };
+  if (PIXMAP == NULL)
+    exit (1);
+  read_sma(argv[2],OUT,PIXMAP,&SM);
 #else
   //  If appropriately named het-mer table found then ask if reuse (PloidyPlot.c:1318-1337)
 
@@ -450,10 +466,10 @@ int main(int argc, char *argv[])
               *o++ = dna[bse];
           }
         *o++ = '\n'; *o = '\0';
-        fputs(line,SMUDGE[q->smudge-1].f);
+        fputs(line,SM.v[q->smudge-1].f);
       }
-    for (i = 0; i < SM_NUM; i++)
-      fclose(SMUDGE[i].f);
+    for (i = 0; i < SM.n; i++)
+      fclose(SM.v[i].f);
     free(REC);
   }
 #else
