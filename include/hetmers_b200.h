@@ -144,6 +144,55 @@ int hm_k_pass2_extract(const uint64_t *d_keys, const uint64_t *d_keys_lo, const 
                        const uint16_t *d_pixmap, hm_pair_rec *d_out, int64_t cap,
                        unsigned long long *d_count, const hm_shards *shards, void *stream);
 
+/* ---- the strand-symmetric scan (csrc/hm_symm.cu): every entry read once ------------------------
+ * On a table that holds rc(x) with count(x) for every x -- what the reference demands before it
+ * scans (examine_table, PloidyPlot.c:1199-1229; `Symmex` otherwise, :1401-1414) -- the pairs that
+ * differ at a low position are mirror images of the pairs that differ at a high position, and those
+ * sit in one short run of neighbouring entries.  hm_k_symm_runscan + hm_k_symm_resolve produce the
+ * same plot as hm_k_pass1_degree + hm_k_pass2_plot (= the reference's two passes) on such a table;
+ * hm_k_symm_fingerprint decides whether a table is one (keyed multiset fingerprints of {(x,cnt)}
+ * and {(rc x,cnt)}: acc[0]==acc[2] && acc[1]==acc[3]); anything else must take the direct passes. */
+#define HM_SYMM_MIN_KMER 2
+
+typedef struct hm_symm_layout               /* work area of one scan range (hm_symm_plan fills it in)     */
+  { int64_t bytes;                          /* device bytes to allocate (256-byte aligned)                */
+    int64_t off_header;                     /* uint64[2]: candidate count, status bits (hm_symm_status)   */
+    int64_t off_bloom;                      /* n_seg segments of seg_words uint32: Bloom filter over the  */
+    int64_t seg_words;                      /*   entries with a partner in their upper half, per shard    */
+    int64_t off_cand_key, off_cand_lo, off_cand_meta;   /* candidate pair records                         */
+    int64_t cand_cap;
+    int64_t range;
+    int32_t n_seg, pad;
+  } hm_symm_layout;
+
+typedef struct hm_symm_shards               /* several GPUs: shard r scans [off[r], off[r+1]) and fills   */
+  { int32_t  n_seg, self;                   /*   Bloom segment r; the segments are all-gathered between   */
+    int64_t  off[HM_MAX_SHARDS+1];          /*   the two kernels.  Cuts lie on run boundaries             */
+    uint64_t first_key[HM_MAX_SHARDS];      /*   (hm_symm_align_cut); first_key[r] = keys[off[r]]         */
+  } hm_symm_shards;
+
+#define HM_SYMM_ASYMMETRIC 1                /* status bit: some rc(x) was not in the table -> result void */
+#define HM_SYMM_OVERFLOW   2                /* status bit: candidate list full (cut not on a run boundary) */
+
+int  hm_symm_plan(int64_t n, int64_t range, int kmer, int n_seg, hm_symm_layout *out);
+void hm_symm_seeds(uint64_t seed[2]);       /* per-process random seeds for the fingerprint               */
+/* adds the fingerprints of entries [i0,i1) to d_acc (device uint64[4], zeroed by the caller)            */
+int  hm_k_symm_fingerprint(const uint64_t *d_keys, const uint64_t *d_keys_lo, const uint16_t *d_cnt,
+                           int64_t i0, int64_t i1, int kmer, const uint64_t seed[2],
+                           uint64_t *d_acc, void *stream);
+/* "pass 1": run scan of [lo,hi): Bloom segment `self` + candidate records (both initialised here).     */
+int  hm_k_symm_runscan(const uint64_t *d_keys, const uint64_t *d_keys_lo, const uint16_t *d_cnt, int64_t n,
+                       const void *d_bucket, int bits, int idx64, int kmer, int64_t lo, int64_t hi,
+                       void *d_work, const hm_symm_layout *layout, const hm_symm_shards *shards, void *stream);
+/* "pass 2": candidates -> isolated pairs -> d_plot (accumulated into; caller zeroes it)                 */
+int  hm_k_symm_resolve(const uint64_t *d_keys, const uint64_t *d_keys_lo, const uint16_t *d_cnt, int64_t n,
+                       const void *d_bucket, int bits, int idx64, int kmer,
+                       void *d_work, const hm_symm_layout *layout, const hm_symm_shards *shards,
+                       unsigned long long *d_plot, void *stream);
+int  hm_symm_status(const void *d_work, const hm_symm_layout *layout, uint64_t *n_cand, uint64_t *status,
+                    void *stream);
+int  hm_symm_align_cut(const uint64_t *d_keys, int64_t n, int kmer, int64_t cut, int64_t *out);
+
 /* Device memory that can be mapped by the other ranks of a one-process-per-GPU job (CUDA IPC):
  * hm_dev_alloc gives a zeroed base allocation on the current device, hm_ipc_export its 64-byte
  * handle (send it to the peers with any host transport), hm_ipc_open maps a peer's allocation.
@@ -190,7 +239,7 @@ typedef struct hm_scan_stats
     int32_t n_gpus;
     int32_t bucket_bits;
     int32_t filter_bits;
-    int32_t reserved;
+    int32_t path;                /* HM_PATH_DIRECT or HM_PATH_SYMM: which scan produced the plot */
     double  ms_h2d_unpack;       /* H2D copies + unpack + bucket index (T_load, device part) */
     double  ms_pass1;
     double  ms_pass2;
@@ -219,9 +268,18 @@ int  hm_scan_examine(hm_scan *s, int ethresh, int *trim, int *symm);
  * count (what `Symmex` does) -- PloidyPlot.c:1381-1426 shells out to those FastK tools; here the
  * table never leaves the GPU.  *nels_out = entries afterwards.                                  */
 int  hm_scan_condition(hm_scan *s, int ethresh, int do_trim, int do_symm, int64_t *nels_out);
-/* both passes; plot: host int64[HM_PLOT_CELLS]; stats optional */
+/* both passes; plot: host int64[HM_PLOT_CELLS]; stats optional.  Tables that hm_scan_create found
+ * strand-symmetric (fingerprint over the whole table) take the symmetric scan of csrc/hm_symm.cu,
+ * all others the direct passes; both give the reference's plot.  hm_scan_run_path forces one
+ * (HM_PATH_SYMM on a table that is not symmetric is an error); HETMERS_PATH=direct|symm overrides
+ * HM_PATH_AUTO.                                                                                  */
+#define HM_PATH_AUTO   0
+#define HM_PATH_DIRECT 1
+#define HM_PATH_SYMM   2
 int  hm_scan_run(hm_scan *s, int64_t *plot, hm_scan_stats *stats);
-/* after hm_scan_run: the pair list of extract_kmer_pairs for a pixel->smudge map (host
+int  hm_scan_run_path(hm_scan *s, int path, int64_t *plot, hm_scan_stats *stats);
+int  hm_scan_is_symmetric(const hm_scan *s);
+/* the pair list of extract_kmer_pairs (runs the direct passes first if the last run did not) for a pixel->smudge map (host
  * uint16[HM_PLOT_CELLS]); *out is malloc'ed (caller frees), sorted by (smudge, k-mer).          */
 int  hm_scan_extract(hm_scan *s, const uint16_t *pixmap, hm_pair_rec **out, int64_t *n_out);
 /* one call: create + run + destroy (what bench.py's e2e leg times) */

@@ -22,6 +22,8 @@ ABI_SYMBOLS = [
     "hm_k_build_filter", "hm_filter_words", "hm_pick_filter_bits",
     "hm_dev_alloc", "hm_dev_free", "hm_ipc_export", "hm_ipc_open", "hm_ipc_close", "hm_p2p_native_atomics",
     "hm_scan_create", "hm_set_io_threads", "hm_scan_destroy", "hm_scan_examine", "hm_scan_condition", "hm_scan_run", "hm_hetmers_host",
+    "hm_scan_run_path", "hm_scan_is_symmetric", "hm_symm_plan", "hm_symm_seeds", "hm_k_symm_fingerprint", "hm_k_symm_runscan", "hm_k_symm_resolve",
+    "hm_symm_status", "hm_symm_align_cut",
     "hm_scan_download", "hm_table_open", "hm_table_close", "hm_table_view", "hm_write_smu",
 ]
 
@@ -42,6 +44,22 @@ class Shards(C.Structure):
                 ("deg", C.c_void_p * MAX_SHARDS), ("scratch", C.c_void_p), ("scratch_bytes", C.c_int64)]
 
 
+class SymmLayout(C.Structure):
+    """hm_symm_layout: work area of the strand-symmetric scan"""
+    _fields_ = [("bytes", C.c_int64), ("off_header", C.c_int64), ("off_bloom", C.c_int64), ("seg_words", C.c_int64),
+                ("off_cand_key", C.c_int64), ("off_cand_lo", C.c_int64), ("off_cand_meta", C.c_int64),
+                ("cand_cap", C.c_int64), ("range", C.c_int64), ("n_seg", C.c_int32), ("pad", C.c_int32)]
+
+
+class SymmShards(C.Structure):
+    """hm_symm_shards: run-aligned shard cuts + the first key of every shard"""
+    _fields_ = [("n_seg", C.c_int32), ("self_", C.c_int32), ("off", C.c_int64 * (MAX_SHARDS + 1)),
+                ("first_key", C.c_uint64 * MAX_SHARDS)]
+
+
+SYMM_ASYMMETRIC, SYMM_OVERFLOW = 1, 2
+
+
 class PairRec(C.Structure):
     """hm_pair_rec: one line of extract_kmer_pairs' output"""
     _fields_ = [("key_hi", C.c_uint64), ("key_lo", C.c_uint64), ("smudge", C.c_uint32),
@@ -50,7 +68,7 @@ class PairRec(C.Structure):
 
 class ScanStats(C.Structure):
     _fields_ = [("nels", C.c_int64), ("n_gpus", C.c_int32), ("bucket_bits", C.c_int32),
-                ("filter_bits", C.c_int32), ("reserved", C.c_int32),
+                ("filter_bits", C.c_int32), ("path", C.c_int32),
                 ("ms_h2d_unpack", C.c_double), ("ms_pass1", C.c_double), ("ms_pass2", C.c_double),
                 ("ms_scan", C.c_double), ("ms_total", C.c_double), ("kernel_launches", C.c_int64),
                 ("ms_alloc", C.c_double), ("ms_records", C.c_double), ("ms_index", C.c_double)]
@@ -99,12 +117,24 @@ def lib():
     L.hm_pick_bucket_bits.argtypes = [i64]
     L.hm_pass2_scratch_bytes.argtypes = [i64, i32]
     L.hm_pass2_scratch_bytes.restype = i64
+    L.hm_symm_plan.argtypes = [i64, i64, i32, i32, C.POINTER(SymmLayout)]
+    L.hm_symm_seeds.argtypes = [C.POINTER(C.c_uint64)]
+    L.hm_symm_seeds.restype = None
+    L.hm_k_symm_fingerprint.argtypes = [vp, vp, vp, i64, i64, i32, C.POINTER(C.c_uint64), vp, vp]
+    L.hm_k_symm_runscan.argtypes = [vp, vp, vp, i64, vp, i32, i32, i32, i64, i64, vp, C.POINTER(SymmLayout),
+                                    C.POINTER(SymmShards), vp]
+    L.hm_k_symm_resolve.argtypes = [vp, vp, vp, i64, vp, i32, i32, i32, vp, C.POINTER(SymmLayout),
+                                    C.POINTER(SymmShards), vp, vp]
+    L.hm_symm_status.argtypes = [vp, C.POINTER(SymmLayout), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), vp]
+    L.hm_symm_align_cut.argtypes = [vp, i64, i32, i64, C.POINTER(i64)]
     L.hm_scan_create.argtypes = [C.POINTER(HostTable), C.POINTER(i32), i32, C.POINTER(vp)]
     L.hm_scan_destroy.argtypes = [vp]
     L.hm_scan_destroy.restype = None
     L.hm_scan_examine.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
     L.hm_scan_condition.argtypes = [vp, i32, i32, i32, C.POINTER(i64)]
     L.hm_scan_run.argtypes = [vp, vp, C.POINTER(ScanStats)]
+    L.hm_scan_run_path.argtypes = [vp, i32, vp, C.POINTER(ScanStats)]
+    L.hm_scan_is_symmetric.argtypes = [vp]
     L.hm_scan_extract.argtypes = [vp, vp, C.POINTER(C.POINTER(PairRec)), C.POINTER(i64)]
     L.hm_hetmers_host.argtypes = [C.POINTER(HostTable), C.POINTER(i32), i32, vp, C.POINTER(ScanStats)]
     L.hm_scan_download.argtypes = [vp, vp, vp, vp, vp]

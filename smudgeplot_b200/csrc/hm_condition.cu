@@ -96,6 +96,7 @@ static int select_flagged(const T *in, const uint8_t *flag, T *out, int64_t n, i
   HM_CUDA(cub::DeviceSelect::Flagged(NULL,need,in,flag,out,d_nsel,n,st));
   if (need > *tmp_bytes)
     { if (*tmp) cudaFree(*tmp);
+      *tmp = NULL; *tmp_bytes = 0;
       HM_CUDA(cudaMalloc(tmp,need));
       *tmp_bytes = need;
     }
@@ -110,6 +111,7 @@ static int sort_pairs(const K *kin, K *kout, const V *vin, V *vout, int64_t n, i
   HM_CUDA(cub::DeviceRadixSort::SortPairs(NULL,need,kin,kout,vin,vout,n,begin_bit,end_bit,st));
   if (need > *tmp_bytes)
     { if (*tmp) cudaFree(*tmp);
+      *tmp = NULL; *tmp_bytes = 0;
       HM_CUDA(cudaMalloc(tmp,need));
       *tmp_bytes = need;
     }
@@ -117,93 +119,125 @@ static int sort_pairs(const K *kin, K *kout, const V *vin, V *vout, int64_t n, i
   return HM_OK;
 }
 
+/* device allocations of one conditioning call: everything still registered is freed on return */
+struct Scratch
+  { void *p[32];
+    int   n;
+    Scratch() : n(0) {}
+    ~Scratch() { for (int k = 0; k < n; k++) cudaFree(p[k]); }
+    template <typename T> cudaError_t alloc(T **q, size_t bytes)
+    { cudaError_t e = cudaMalloc((void **) q,bytes);
+      if (e == cudaSuccess && n < 32) p[n++] = (void *) *q;
+      return e;
+    }
+    void release(void *q)                      /* hand q to the caller (or it was freed by hand) */
+    { for (int k = 0; k < n; k++)
+        if (p[k] == q) { p[k] = p[--n]; return; }
+    }
+    void free_now(void *q) { if (q != NULL) { release(q); cudaFree(q); } }
+  };
+
 /* Replace (*pk, *pl, *pc, *pn) by the conditioned table (new cudaMalloc'ed arrays with one spare
- * element; the old ones are freed).  *pl is NULL for k <= 32.                                  */
+ * element).  *pl is NULL for k <= 32.  The caller's arrays are freed and replaced only when the whole
+ * call has succeeded; on any failure they are untouched and every temporary is released.        */
 int hm_condition_arrays(int kmer, int ethresh, int do_trim, int do_symm,
                         uint64_t **pk, uint64_t **pl, uint16_t **pc, int64_t *pn, cudaStream_t st)
 { int64_t   n = *pn;
-  int       two = (*pl != NULL);
-  void     *tmp = NULL;
+  const int two = (*pl != NULL);
+  Scratch   S;
+  void     *tmp = NULL;                        /* CUB temporary storage (grown on demand) */
   size_t    tmp_bytes = 0;
   uint8_t  *flag = NULL;
   int64_t  *d_nsel = NULL, nsel = 0;
   int       rc = HM_OK;
+  /* current table: the caller's arrays, or ours once a stage has produced new ones */
+  uint64_t *ck = *pk, *cl = *pl;
+  uint16_t *cc = *pc;
+  int       own = 0;
 
-  HM_CUDA(cudaMalloc(&d_nsel,sizeof(int64_t)));
+  if (do_symm && two && 2*n >= 0xFFFFFFF0ll)   /* before anything is allocated or touched */
+    return hm_set_error(HM_EUNSUPPORTED,"symmetrising %lld entries of k=%d needs 64-bit sort indices",
+                        (long long) n,kmer);
+#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { if (tmp) cudaFree(tmp); return hm_cuda_fail(_e,#call); } } while (0)
+#define RC(call) do { if ((rc = (call)) != HM_OK) { if (tmp) cudaFree(tmp); return rc; } } while (0)
+  CK(S.alloc(&d_nsel,sizeof(int64_t)));
 
   if (do_trim && n > 0)
     { uint64_t *k2 = NULL, *l2 = NULL; uint16_t *c2 = NULL;
-      HM_CUDA(cudaMalloc(&flag,(size_t) n));
-      HM_CUDA(cudaMalloc(&k2,sizeof(uint64_t)*(size_t) (n+1)));
-      HM_CUDA(cudaMalloc(&c2,sizeof(uint16_t)*(size_t) (n+1)));
-      if (two) HM_CUDA(cudaMalloc(&l2,sizeof(uint64_t)*(size_t) (n+1)));
-      trim_flag_kernel<<<GRID(n),256,0,st>>>(*pc,n,ethresh,flag);
-      if ((rc = select_flagged(*pk,flag,k2,n,d_nsel,&tmp,&tmp_bytes,st)) != HM_OK) return rc;
-      if (two && (rc = select_flagged(*pl,flag,l2,n,d_nsel,&tmp,&tmp_bytes,st)) != HM_OK) return rc;
-      if ((rc = select_flagged(*pc,flag,c2,n,d_nsel,&tmp,&tmp_bytes,st)) != HM_OK) return rc;
-      HM_CUDA(cudaMemcpyAsync(&nsel,d_nsel,sizeof(int64_t),cudaMemcpyDeviceToHost,st));
-      HM_CUDA(cudaStreamSynchronize(st));
-      cudaFree(*pk); cudaFree(*pc); if (two) cudaFree(*pl);
-      cudaFree(flag); flag = NULL;
-      *pk = k2; *pc = c2; *pl = l2; n = nsel;
+      CK(S.alloc(&flag,(size_t) n));
+      CK(S.alloc(&k2,sizeof(uint64_t)*(size_t) (n+1)));
+      CK(S.alloc(&c2,sizeof(uint16_t)*(size_t) (n+1)));
+      if (two) CK(S.alloc(&l2,sizeof(uint64_t)*(size_t) (n+1)));
+      trim_flag_kernel<<<GRID(n),256,0,st>>>(cc,n,ethresh,flag);
+      RC(select_flagged(ck,flag,k2,n,d_nsel,&tmp,&tmp_bytes,st));
+      if (two) RC(select_flagged(cl,flag,l2,n,d_nsel,&tmp,&tmp_bytes,st));
+      RC(select_flagged(cc,flag,c2,n,d_nsel,&tmp,&tmp_bytes,st));
+      CK(cudaMemcpyAsync(&nsel,d_nsel,sizeof(int64_t),cudaMemcpyDeviceToHost,st));
+      CK(cudaStreamSynchronize(st));
+      S.free_now(flag); flag = NULL;
+      ck = k2; cc = c2; cl = l2; n = nsel; own = 1;
     }
 
   if (do_symm && n > 0)
     { int64_t   m = 2*n;
       uint64_t *h0 = NULL, *l0 = NULL, *h1 = NULL, *l1 = NULL;
       uint16_t *c0 = NULL, *c1 = NULL;
-      if (m >= 0xFFFFFFF0ll)
-        return hm_set_error(HM_EUNSUPPORTED,"symmetrising %lld entries needs 64-bit sort indices",(long long) n);
-      HM_CUDA(cudaMalloc(&h0,sizeof(uint64_t)*(size_t) (m+1)));
-      HM_CUDA(cudaMalloc(&h1,sizeof(uint64_t)*(size_t) (m+1)));
-      HM_CUDA(cudaMalloc(&c0,sizeof(uint16_t)*(size_t) (m+1)));
-      HM_CUDA(cudaMalloc(&c1,sizeof(uint16_t)*(size_t) (m+1)));
+      CK(S.alloc(&h0,sizeof(uint64_t)*(size_t) (m+1)));
+      CK(S.alloc(&h1,sizeof(uint64_t)*(size_t) (m+1)));
+      CK(S.alloc(&c0,sizeof(uint16_t)*(size_t) (m+1)));
+      CK(S.alloc(&c1,sizeof(uint16_t)*(size_t) (m+1)));
       if (two)
-        { HM_CUDA(cudaMalloc(&l0,sizeof(uint64_t)*(size_t) (m+1)));
-          HM_CUDA(cudaMalloc(&l1,sizeof(uint64_t)*(size_t) (m+1)));
+        { CK(S.alloc(&l0,sizeof(uint64_t)*(size_t) (m+1)));
+          CK(S.alloc(&l1,sizeof(uint64_t)*(size_t) (m+1)));
         }
-      append_revcomp_kernel<<<GRID(n),256,0,st>>>(*pk,*pl,*pc,n,kmer,h0,l0,c0);
-      cudaFree(*pk); cudaFree(*pc); if (two) cudaFree(*pl);
-      *pk = NULL; *pc = NULL; *pl = NULL;
+      append_revcomp_kernel<<<GRID(n),256,0,st>>>(ck,cl,cc,n,kmer,h0,l0,c0);
+      if (own)                                       /* the trimmed intermediate is ours: drop it now */
+        { CK(cudaStreamSynchronize(st));
+          S.free_now(ck); S.free_now(cc); S.free_now(cl);
+          ck = NULL; cc = NULL; cl = NULL; own = 0;
+        }
       if (!two)
         { int bb = kmer < 32 ? 64-2*kmer : 0;
-          if ((rc = sort_pairs(h0,h1,c0,c1,m,bb,64,&tmp,&tmp_bytes,st)) != HM_OK) return rc;
+          RC(sort_pairs(h0,h1,c0,c1,m,bb,64,&tmp,&tmp_bytes,st));
         }
       else
         { uint32_t *i0 = NULL, *i1 = NULL;
-          HM_CUDA(cudaMalloc(&i0,sizeof(uint32_t)*(size_t) m));
-          HM_CUDA(cudaMalloc(&i1,sizeof(uint32_t)*(size_t) m));
+          CK(S.alloc(&i0,sizeof(uint32_t)*(size_t) m));
+          CK(S.alloc(&i1,sizeof(uint32_t)*(size_t) m));
           iota_kernel<<<GRID(m),256,0,st>>>(i0,m);
           int bb = kmer < 64 ? 128-2*kmer : 0;
           /* least significant word first, then a stable sort on the most significant word */
-          if ((rc = sort_pairs(l0,l1,i0,i1,m,bb,64,&tmp,&tmp_bytes,st)) != HM_OK) return rc;
+          RC(sort_pairs(l0,l1,i0,i1,m,bb,64,&tmp,&tmp_bytes,st));
           gather_kernel<uint64_t><<<GRID(m),256,0,st>>>(h0,i1,m,h1);          /* hi in lo-order   */
-          if ((rc = sort_pairs(h1,l1,i1,i0,m,0,64,&tmp,&tmp_bytes,st)) != HM_OK) return rc;
+          RC(sort_pairs(h1,l1,i1,i0,m,0,64,&tmp,&tmp_bytes,st));
           /* l1 = sorted hi, i0 = final permutation */
           gather_kernel<uint64_t><<<GRID(m),256,0,st>>>(l0,i0,m,h1);          /* h1 := lo sorted  */
           gather_kernel<uint16_t><<<GRID(m),256,0,st>>>(c0,i0,m,c1);
           /* arrange as (h1 = hi, l1 = lo) */
           uint64_t *t = h1; h1 = l1; l1 = t;
-          cudaFree(i0); cudaFree(i1);
+          CK(cudaStreamSynchronize(st));
+          S.free_now(i0); S.free_now(i1);
         }
       /* unique (first of every run of equal keys wins) back into h0/l0/c0 */
-      HM_CUDA(cudaMalloc(&flag,(size_t) m));
+      CK(S.alloc(&flag,(size_t) m));
       first_of_run_kernel<<<GRID(m),256,0,st>>>(h1,two ? l1 : NULL,m,flag);
-      if ((rc = select_flagged(h1,flag,h0,m,d_nsel,&tmp,&tmp_bytes,st)) != HM_OK) return rc;
-      if (two && (rc = select_flagged(l1,flag,l0,m,d_nsel,&tmp,&tmp_bytes,st)) != HM_OK) return rc;
-      if ((rc = select_flagged(c1,flag,c0,m,d_nsel,&tmp,&tmp_bytes,st)) != HM_OK) return rc;
-      HM_CUDA(cudaMemcpyAsync(&nsel,d_nsel,sizeof(int64_t),cudaMemcpyDeviceToHost,st));
-      HM_CUDA(cudaStreamSynchronize(st));
-      cudaFree(h1); cudaFree(c1); if (two) cudaFree(l1);
-      cudaFree(flag); flag = NULL;
-      *pk = h0; *pc = c0; *pl = l0; n = nsel;
+      RC(select_flagged(h1,flag,h0,m,d_nsel,&tmp,&tmp_bytes,st));
+      if (two) RC(select_flagged(l1,flag,l0,m,d_nsel,&tmp,&tmp_bytes,st));
+      RC(select_flagged(c1,flag,c0,m,d_nsel,&tmp,&tmp_bytes,st));
+      CK(cudaMemcpyAsync(&nsel,d_nsel,sizeof(int64_t),cudaMemcpyDeviceToHost,st));
+      CK(cudaStreamSynchronize(st));
+      ck = h0; cc = c0; cl = l0; n = nsel; own = 1;
     }
 
-  cudaError_t e = cudaStreamSynchronize(st);
+  CK(cudaStreamSynchronize(st));
+#undef CK
+#undef RC
   if (tmp) cudaFree(tmp);
-  cudaFree(d_nsel);
-  if (e != cudaSuccess)
-    return hm_cuda_fail(e,"conditioning");
+  if (own)                                           /* success: swap the new table in */
+    { S.release(ck); S.release(cc); if (cl) S.release(cl);
+      cudaFree(*pk); cudaFree(*pc); if (*pl) cudaFree(*pl);
+      *pk = ck; *pc = cc; *pl = cl;
+    }
   *pn = n;
   return HM_OK;
 }

@@ -21,6 +21,7 @@
 
 #include "hetmers_b200.h"
 #include "hm_internal.h"
+#include "hm_device.cuh"
 
 /* ------------------------------------------------------------------ error plumbing ------ */
 
@@ -71,8 +72,6 @@ extern "C" int hm_pick_bucket_bits(int64_t n)
 
 /* ------------------------------------------------------------------ device helpers ------ */
 
-template <typename IdxT> struct IdxNone { static constexpr IdxT value = (IdxT) ~(IdxT) 0; };
-
 /* Filter words are streamed (each probed column walks the bitmap once, no reuse), everything else
  * pass 1 touches (keys, bucket offsets, counts) is re-read by neighbouring probes: ask L2 to drop
  * the former first.  P1_FILTER_LD=0 plain __ldg, 1 L2::evict_first, 2 + L1::no_allocate.        */
@@ -101,37 +100,6 @@ __device__ __forceinline__ uint32_t ld_filter(const uint32_t *p, uint64_t pol)
   (void) pol;
   return __ldg(p);
 #endif
-}
-
-/* exact match of y inside its prefix bucket; -1 if absent.  KW = 64-bit words per key (k <= 32: 1,
- * k <= 64: 2, second word in the parallel array keys_lo); buckets are prefixes of the first word. */
-template <typename IdxT, int KW>
-__device__ __forceinline__ int64_t bucket_find(const uint64_t *__restrict__ keys,
-                                               const uint64_t *__restrict__ keys_lo,
-                                               const IdxT *__restrict__ bucket,
-                                               int bshift, uint64_t y, uint64_t ylo)
-{ uint64_t bk = y >> bshift;
-  IdxT l = bucket[bk];
-  IdxT r = bucket[bk+1];
-  while (l < r)
-    { IdxT     m = l + ((r-l)>>1);
-      uint64_t v = __ldg(keys+m);
-      if (KW == 1)
-        { if (v == y)
-            return (int64_t) m;
-          if (v < y) l = m+1; else r = m;
-        }
-      else
-        { if (v == y)
-            { uint64_t w = __ldg(keys_lo+m);
-              if (w == ylo)
-                return (int64_t) m;
-              if (w < ylo) l = m+1; else r = m;
-            }
-          else if (v < y) l = m+1; else r = m;
-        }
-    }
-  return -1;
 }
 
 /* ------------------------------------------------------------------------- unpack ------- */
@@ -186,32 +154,6 @@ unpack_records_kernel(const uint8_t *__restrict__ rec, int64_t n, int64_t first,
  * fields are then picked out of shared memory; keys/counts leave as coalesced 8- / 2-byte stores.
  * Needs a 16-byte aligned source (tile size UNP_TILE*pbyte is a multiple of 16 by construction). */
 #define UNP_TILE 1024
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p)
-{ return (uint32_t) __cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
-{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory"); }
-
-__device__ __forceinline__ void fence_proxy_async_smem(void)
-{ asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes)
-{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-               :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
-
-__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
-{ asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :: "r"(smem_u32(dst)), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
-               : "memory"); }
-
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
-{ unsigned ok;
-  do
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  while (!ok);
-}
 
 __global__ void __launch_bounds__(256)
 unpack_records_tma_kernel(const uint8_t *__restrict__ rec, int64_t first,

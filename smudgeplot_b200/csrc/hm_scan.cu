@@ -23,6 +23,7 @@
 #include <time.h>
 #include <pthread.h>
 #include <unistd.h>
+#include <errno.h>
 
 #include "hetmers_b200.h"
 #include "hm_internal.h"
@@ -44,6 +45,10 @@ typedef struct
     int64_t             p2scratch_bytes;
     unsigned long long *plot;
     int64_t             lo, hi;       /* this device's work range */
+    void               *symm_work;    /* work area of the strand-symmetric scan (hm_symm.cu) */
+    hm_symm_layout      symm_layout;
+    int64_t             slo, shi;     /* its run-aligned range */
+    uint64_t           *fp_acc;       /* device uint64[4]: symmetry fingerprint sums of the entries loaded here */
   } DevTable;
 
 struct hm_scan
@@ -51,9 +56,16 @@ struct hm_scan
     int64_t  n;
     DevTable d[HM_MAX_GPUS];
     double   ms_load, ms_alloc, ms_records, ms_index;
-    int      ran, peer_mode;              /* state of the last hm_scan_run */
+    int      ran, peer_mode;              /* ran: the direct passes have filled deg/up (extract, download) */
     hm_shards sh[HM_MAX_GPUS];
     int64_t  launches;
+    int      symmetric;                   /* fingerprint verdict: every rc(x) present with count(x)        */
+    int      have_direct;                 /* deg / up / filter allocated and the filter built               */
+    int      have_symm;                   /* symmetric-scan work areas allocated, cuts aligned              */
+    int      last_path;                   /* HM_PATH_DIRECT / HM_PATH_SYMM of the last run                  */
+    int      invalid;                     /* a failed conditioning left the replicas inconsistent            */
+    hm_symm_shards ssh[HM_MAX_GPUS];
+    uint64_t seed[2];
   };
 
 static double now_ms(void)
@@ -123,7 +135,9 @@ static void free_dev(DevTable *D)
   dfree(D->dev,D->st,D->keys);  dfree(D->dev,D->st,D->keys_lo); dfree(D->dev,D->st,D->cnt);
   dfree(D->dev,D->st,D->deg);   dfree(D->dev,D->st,D->bucket);  dfree(D->dev,D->st,D->filter);
   dfree(D->dev,D->st,D->up);    dfree(D->dev,D->st,D->plot);
+  dfree(D->dev,D->st,D->fp_acc);
   if (D->p2scratch) cudaFree(D->p2scratch);
+  if (D->symm_work) cudaFree(D->symm_work);
   if (D->st) cudaStreamSynchronize(D->st);
   if (D->st)      cudaStreamDestroy(D->st);
   if (D->st_copy) cudaStreamDestroy(D->st_copy);
@@ -147,27 +161,28 @@ static int g_io_threads = 0;
 
 extern "C" void hm_set_io_threads(int n) { g_io_threads = n; }
 
-typedef struct { uint8_t *dst; const uint8_t *src; size_t bytes; int fd; int64_t off; } CopyJob;
+typedef struct { uint8_t *dst; const uint8_t *src; size_t bytes; int fd; int64_t off; int err; } CopyJob;
 
 static void *copy_worker(void *arg)
 { CopyJob *j = (CopyJob *) arg;
+  j->err = 0;
   if (j->fd < 0)
     memcpy(j->dst,j->src,j->bytes);
   else
     { size_t got = 0;                                   /* page cache -> pinned buffer, no mapping */
       while (got < j->bytes)
         { ssize_t r = pread(j->fd,j->dst+got,j->bytes-got,j->off+(int64_t) got);
-          if (r <= 0) break;
+          if (r < 0 && errno == EINTR) continue;
+          if (r <= 0) { j->err = (r < 0) ? errno : -1; break; }    /* -1: file shorter than its header says */
           got += (size_t) r;
         }
-      if (got < j->bytes)
-        memset(j->dst+got,0,j->bytes-got);
     }
   return NULL;
 }
 
-/* fill dst[0,bytes) from memory `src` (fd < 0) or from file `fd` at `off`, with the I/O threads */
-static void parallel_fill(uint8_t *dst, const uint8_t *src, int fd, int64_t foff, size_t bytes)
+/* fill dst[0,bytes) from memory `src` (fd < 0) or from file `fd` at `off`, with the I/O threads;
+ * 0, or the errno (-1 = short file) of the first slice that could not be read                  */
+static int parallel_fill(uint8_t *dst, const uint8_t *src, int fd, int64_t foff, size_t bytes)
 { int nt = g_io_threads;
   if (nt <= 0)
     { long c = sysconf(_SC_NPROCESSORS_ONLN);
@@ -177,22 +192,31 @@ static void parallel_fill(uint8_t *dst, const uint8_t *src, int fd, int64_t foff
   if (bytes < ((size_t) 4<<20)) nt = 1;
   pthread_t th[64];
   CopyJob   job[64];
+  int       created[64];
   size_t    per = ((bytes/nt)+4095) & ~(size_t) 4095;
-  int       started = 0;
+  int       njob = 0, err = 0;
   for (int k = 0; k < nt; k++)
     { size_t off = per*k;
       if (off >= bytes) break;
       job[k].dst = dst+off; job[k].src = src ? src+off : NULL;
       job[k].fd = fd; job[k].off = foff+(int64_t) off;
       job[k].bytes = bytes-off < per ? bytes-off : per;
+      created[k] = 0;
+      njob = k+1;
       if (k == nt-1 || off+per >= bytes)
         { copy_worker(job+k); break; }                 /* the calling thread takes the last slice */
       if (pthread_create(th+k,NULL,copy_worker,job+k) != 0)
-        { copy_worker(job+k); continue; }
-      started = k+1;
+        copy_worker(job+k);                            /* no thread to be had: copy inline */
+      else
+        created[k] = 1;
     }
-  for (int k = 0; k < started; k++)
-    pthread_join(th[k],NULL);
+  for (int k = 0; k < njob; k++)
+    { if (created[k])
+        pthread_join(th[k],NULL);
+      if (job[k].err != 0 && err == 0)
+        err = job[k].err;
+    }
+  return err;
 }
 
 static int is_pageable(const void *p)
@@ -233,11 +257,9 @@ static int load_range(hm_scan *s, DevTable *D, const hm_host_table *t, const int
       HM_CUDA(cudaEventCreateWithFlags(&copied[i],cudaEventDisableTiming));
       HM_CUDA(cudaEventCreateWithFlags(&unpacked[i],cudaEventDisableTiming));
     }
-  /* one GPU: the whole table arrives here in order, so the bucket index and the prefix filter are
-   * built chunk by chunk right behind the unpack (hidden behind the next chunk's H2D)           */
+  /* one GPU: the whole table arrives here in order, so the bucket index is built chunk by chunk
+   * right behind the unpack (hidden behind the next chunk's H2D); so is the symmetry fingerprint   */
   const int inc = (s->ngpu == 1 && first == 0 && count == s->n);
-  if (inc)
-    HM_CUDA(cudaMemsetAsync(D->filter,0,sizeof(uint32_t)*(size_t) hm_filter_words(s->fpos),D->st));
   HM_CUDA(cudaStreamSynchronize(D->st));         /* (pool) allocations are used on both streams */
   int64_t pstart = 0;                               /* ordinal of the part's first record */
   for (int p = 0; p < t->nparts && rc == HM_OK; p++)
@@ -250,10 +272,16 @@ static int load_range(hm_scan *s, DevTable *D, const hm_host_table *t, const int
           if (staged)
             { if (used[b])
                 cudaEventSynchronize(copied[b]);      /* pin[b] has left for the GPU */
+              int ferr;
               if (t->part_fd != NULL && t->part_fd[p] >= 0)
-                parallel_fill(pin[b],NULL,t->part_fd[p],t->part_fd_off[p]+(o-pstart)*pbyte,(size_t) m*pbyte);
+                ferr = parallel_fill(pin[b],NULL,t->part_fd[p],t->part_fd_off[p]+(o-pstart)*pbyte,(size_t) m*pbyte);
               else
-                parallel_fill(pin[b],src,-1,0,(size_t) m*pbyte);
+                ferr = parallel_fill(pin[b],src,-1,0,(size_t) m*pbyte);
+              if (ferr != 0)
+                { rc = hm_set_error(HM_EIO,"short read on part %d of the table (%s)",p+1,
+                                    ferr > 0 ? strerror(ferr) : "file truncated");
+                  break;
+                }
               src = pin[b];
             }
           if (used[b])
@@ -264,13 +292,15 @@ static int load_range(hm_scan *s, DevTable *D, const hm_host_table *t, const int
           cudaStreamWaitEvent(D->st,copied[b],0);
           rc = hm_k_unpack_records(stage[b],m,o,d_index,t->ibyte,t->kmer,D->keys+o,
                                    D->keys_lo ? D->keys_lo+o : NULL,D->cnt+o,D->st);
-          s->launches += 1;
+          __sync_fetch_and_add(&s->launches,1);
           cudaEventRecord(unpacked[b],D->st);
           if (inc && rc == HM_OK)
             { rc = hm_build_bucket_index_range(D->keys,s->n,s->bits,D->bucket,s->idx64,o,o+m,D->st);
-              if (rc == HM_OK)
-                rc = hm_build_filter_range(D->keys,s->fpos,D->filter,o,o+m,D->st);
-              s->launches += 2;
+              __sync_fetch_and_add(&s->launches,1);
+            }
+          if (rc == HM_OK && s->kmer >= HM_SYMM_MIN_KMER)       /* symmetry fingerprint of what this device loads */
+            { rc = hm_k_symm_fingerprint(D->keys,D->keys_lo,D->cnt,o,o+m,s->kmer,s->seed,D->fp_acc,D->st);
+              __sync_fetch_and_add(&s->launches,1);
             }
           used[b] = 1;
           b ^= 1;
@@ -286,6 +316,47 @@ static int load_range(hm_scan *s, DevTable *D, const hm_host_table *t, const int
   if (rc == HM_OK && e != cudaSuccess)
     rc = hm_cuda_fail(e,"unpack");
   return rc;
+}
+
+/* one host thread per device: stub index upload + this device's shard of the records */
+typedef struct { hm_scan *s; int g; const hm_host_table *t; int rc; char msg[512]; } LoadJob;
+
+static void *load_worker(void *arg)
+{ LoadJob  *J = (LoadJob *) arg;
+  hm_scan  *s = J->s;
+  DevTable *D = s->d+J->g;
+  int64_t  *d_index = NULL;
+  int64_t   ixlen = (int64_t) 1 << (8*J->t->ibyte);
+  J->rc = HM_OK;
+  cudaError_t e = cudaSetDevice(D->dev);
+  if (e == cudaSuccess) e = dalloc(D->dev,D->st,(void **) &d_index,sizeof(int64_t)*ixlen);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_index,J->t->index,sizeof(int64_t)*ixlen,cudaMemcpyHostToDevice,D->st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(D->fp_acc,0,4*sizeof(uint64_t),D->st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(D->st);     /* pool memory is about to be used on the copy stream too */
+  if (e != cudaSuccess)
+    J->rc = hm_cuda_fail(e,"stub index upload");
+  else
+    J->rc = load_range(s,D,J->t,d_index,D->lo,D->hi-D->lo);
+  if (d_index != NULL) dfree(D->dev,D->st,d_index);
+  if (J->rc != HM_OK)
+    { strncpy(J->msg,hm_last_error(),sizeof(J->msg)-1); J->msg[sizeof(J->msg)-1] = 0; }
+  return NULL;
+}
+
+/* sum of the per-device fingerprint accumulators -> s->symmetric */
+static int fingerprint_verdict(hm_scan *s)
+{ uint64_t tot[4] = {0,0,0,0};
+  if (s->kmer < HM_SYMM_MIN_KMER)
+    { s->symmetric = 0; return HM_OK; }
+  for (int g = 0; g < s->ngpu; g++)
+    { uint64_t h[4];
+      HM_CUDA(cudaSetDevice(s->d[g].dev));
+      HM_CUDA(cudaMemcpyAsync(h,s->d[g].fp_acc,sizeof(h),cudaMemcpyDeviceToHost,s->d[g].st));
+      HM_CUDA(cudaStreamSynchronize(s->d[g].st));
+      for (int k = 0; k < 4; k++) tot[k] += h[k];
+    }
+  s->symmetric = (tot[0] == tot[2] && tot[1] == tot[3]);
+  return HM_OK;
 }
 
 extern "C" int hm_scan_create(const hm_host_table *t, const int *dev, int n_gpus, hm_scan **out)
@@ -308,14 +379,16 @@ extern "C" int hm_scan_create(const hm_host_table *t, const int *dev, int n_gpus
   s->bits  = hm_pick_bucket_bits(s->n);
   s->fpos  = hm_pick_filter_bits(s->n);
   s->idx64 = (s->n >= 0xFFFFFFF0ll);
+  hm_symm_seeds(s->seed);
   int64_t n  = s->n;
   size_t  ib = s->idx64 ? 8 : 4;
-  int64_t ixlen = (int64_t) 1 << (8*t->ibyte);
   int     rc = HM_OK;
 
   if (n_gpus > 1 && (rc = hm_peer_enable(dev,n_gpus)) != HM_OK)
     { free(s); return rc; }
 
+  /* table arrays + bucket index; the work buffers of either scan path are allocated by the path
+   * that runs (ensure_direct / ensure_symm)                                                     */
   for (int g = 0; g < n_gpus && rc == HM_OK; g++)
     { DevTable *D = s->d+g;
       D->dev = dev ? dev[g] : g;
@@ -330,29 +403,33 @@ extern "C" int hm_scan_create(const hm_host_table *t, const int *dev, int n_gpus
       TRY(dalloc(D->dev,D->st,(void **) &D->keys,sizeof(uint64_t)*(size_t) (n+1)));
       if (t->kmer > 32)
         TRY(dalloc(D->dev,D->st,(void **) &D->keys_lo,sizeof(uint64_t)*(size_t) (n+1)));
-      TRY(dalloc(D->dev,D->st,(void **) &D->cnt,sizeof(uint16_t)*(size_t) (n+1)));
-      TRY(dalloc(D->dev,D->st,(void **) &D->deg,(size_t) ((n+4)&~3ll)));
+      TRY(dalloc(D->dev,D->st,(void **) &D->cnt,sizeof(uint16_t)*(size_t) (n+8)));
       TRY(dalloc(D->dev,D->st,(void **) &D->bucket,ib*(((size_t) 1<<s->bits)+1)));
-      TRY(dalloc(D->dev,D->st,(void **) &D->filter,sizeof(uint32_t)*(size_t) hm_filter_words(s->fpos)));
-      TRY(dalloc(D->dev,D->st,(void **) &D->up,ib*(size_t) (D->hi-D->lo+1)));
       TRY(dalloc(D->dev,D->st,(void **) &D->plot,sizeof(unsigned long long)*HM_PLOT_CELLS));
+      TRY(dalloc(D->dev,D->st,(void **) &D->fp_acc,4*sizeof(uint64_t)));
 #undef TRY
     }
 
   double t_alloc = now_ms();
-  /* each device unpacks its own shard from the host, then the shards are exchanged over peer
-   * copies so that every device ends with the full table                                      */
-  for (int g = 0; g < n_gpus && rc == HM_OK; g++)
-    { DevTable *D = s->d+g;
-      int64_t  *d_index = NULL;
-      cudaSetDevice(D->dev);
-      cudaError_t e = dalloc(D->dev,D->st,(void **) &d_index,sizeof(int64_t)*ixlen);
-      if (e != cudaSuccess) { rc = hm_cuda_fail(e,"cudaMalloc(stub index)"); break; }
-      e = cudaMemcpyAsync(d_index,t->index,sizeof(int64_t)*ixlen,cudaMemcpyHostToDevice,D->st);
-      if (e != cudaSuccess) { rc = hm_cuda_fail(e,"cudaMemcpyAsync(stub index)"); dfree(D->dev,D->st,d_index); break; }
-      cudaStreamSynchronize(D->st);          /* pool memory is about to be used on the copy stream too */
-      rc = load_range(s,D,t,d_index,D->lo,D->hi-D->lo);
-      dfree(D->dev,D->st,d_index);
+  /* each device unpacks its own shard from the host -- all devices at once, one host thread each --
+   * then the shards are exchanged over peer copies so that every device ends with the full table */
+  if (rc == HM_OK)
+    { LoadJob   job[HM_MAX_GPUS];
+      pthread_t th[HM_MAX_GPUS];
+      int       created[HM_MAX_GPUS];
+      for (int g = 0; g < n_gpus; g++)
+        { job[g].s = s; job[g].g = g; job[g].t = t; job[g].rc = HM_OK; job[g].msg[0] = 0;
+          created[g] = 0;
+          if (g == n_gpus-1 || pthread_create(th+g,NULL,load_worker,job+g) != 0)
+            load_worker(job+g);                              /* the calling thread takes the last device */
+          else
+            created[g] = 1;
+        }
+      for (int g = 0; g < n_gpus; g++)
+        { if (created[g]) pthread_join(th[g],NULL);
+          if (job[g].rc != HM_OK && rc == HM_OK)
+            rc = hm_set_error(job[g].rc,"%s",job[g].msg);
+        }
     }
   double t_rec = now_ms();
   if (n_gpus > 1 && rc == HM_OK)
@@ -380,20 +457,85 @@ extern "C" int hm_scan_create(const hm_host_table *t, const int *dev, int n_gpus
     { DevTable *D = s->d+g;
       cudaSetDevice(D->dev);
       rc = hm_k_build_bucket_index(D->keys,n,s->bits,D->bucket,s->idx64,D->st);
-      if (rc == HM_OK)
-        rc = hm_k_build_filter(D->keys,n,s->fpos,D->filter,D->st);
-      s->launches += 2;
+      s->launches += 1;
     }
   for (int g = 0; g < n_gpus; g++)
     { cudaSetDevice(s->d[g].dev);
       cudaError_t e = cudaStreamSynchronize(s->d[g].st);
       if (rc == HM_OK && e != cudaSuccess) rc = hm_cuda_fail(e,"table load");
     }
+  if (rc == HM_OK)
+    rc = fingerprint_verdict(s);
   if (rc != HM_OK)
     { hm_scan_destroy(s); return rc; }
   s->ms_load = now_ms()-t0;
   s->ms_alloc = t_alloc-t0; s->ms_records = t_rec-t_alloc; s->ms_index = now_ms()-t_rec;
   *out = s;
+  return HM_OK;
+}
+
+/* work buffers of the direct passes (hm_kernels.cu): incidence array, recorded partners, prefix filter */
+static int ensure_direct(hm_scan *s)
+{ if (s->have_direct)
+    return HM_OK;
+  int64_t n  = s->n;
+  size_t  ib = s->idx64 ? 8 : 4;
+  int     rc = HM_OK;
+  for (int g = 0; g < s->ngpu && rc == HM_OK; g++)
+    { DevTable *D = s->d+g;
+      cudaError_t e;
+#define TRY(call) if (rc == HM_OK && (e = (call)) != cudaSuccess) rc = hm_cuda_fail(e,#call)
+      TRY(cudaSetDevice(D->dev));
+      if (D->deg == NULL)    TRY(dalloc(D->dev,D->st,(void **) &D->deg,(size_t) ((n+4)&~3ll)));
+      if (D->up == NULL)     TRY(dalloc(D->dev,D->st,(void **) &D->up,ib*(size_t) (D->hi-D->lo+1)));
+      if (D->filter == NULL) TRY(dalloc(D->dev,D->st,(void **) &D->filter,sizeof(uint32_t)*(size_t) hm_filter_words(s->fpos)));
+#undef TRY
+      if (rc == HM_OK)
+        rc = hm_k_build_filter(D->keys,n,s->fpos,D->filter,D->st);
+      s->launches += 1;
+    }
+  for (int g = 0; g < s->ngpu; g++)
+    { cudaSetDevice(s->d[g].dev);
+      cudaError_t e = cudaStreamSynchronize(s->d[g].st);
+      if (rc == HM_OK && e != cudaSuccess) rc = hm_cuda_fail(e,"prefix filter");
+    }
+  if (rc == HM_OK)
+    s->have_direct = 1;
+  return rc;
+}
+
+/* work areas of the strand-symmetric scan (hm_symm.cu); several GPUs: cuts on run boundaries */
+static int ensure_symm(hm_scan *s)
+{ if (s->have_symm)
+    return HM_OK;
+  int     G = s->ngpu;
+  int64_t n = s->n, cut[HM_MAX_GPUS+1];
+  cut[0] = 0; cut[G] = n;
+  HM_CUDA(cudaSetDevice(s->d[0].dev));
+  for (int g = 1; g < G; g++)
+    { int rc = hm_symm_align_cut(s->d[0].keys,n,s->kmer,n*g/G,&cut[g]);
+      if (rc != HM_OK) return rc;
+      if (cut[g] < cut[g-1]) cut[g] = cut[g-1];
+    }
+  for (int g = 0; g < G; g++)
+    { DevTable *D = s->d+g;
+      hm_symm_shards *sh = s->ssh+g;
+      memset(sh,0,sizeof(*sh));
+      sh->n_seg = G; sh->self = g;
+      for (int r = 0; r <= G; r++) sh->off[r] = cut[r];
+      HM_CUDA(cudaSetDevice(D->dev));
+      for (int r = 1; r < G; r++)
+        if (cut[r] < n)
+          HM_CUDA(cudaMemcpy(&sh->first_key[r],D->keys+cut[r],sizeof(uint64_t),cudaMemcpyDeviceToHost));
+        else
+          sh->first_key[r] = ~0ull;
+      D->slo = cut[g]; D->shi = cut[g+1];
+      int rc = hm_symm_plan(n,D->shi-D->slo,s->kmer,G,&D->symm_layout);
+      if (rc != HM_OK) return rc;
+      if (D->symm_work != NULL) { cudaFree(D->symm_work); D->symm_work = NULL; }
+      HM_CUDA(cudaMalloc(&D->symm_work,(size_t) D->symm_layout.bytes));
+    }
+  s->have_symm = 1;
   return HM_OK;
 }
 
@@ -404,68 +546,82 @@ extern "C" int hm_scan_create(const hm_host_table *t, const int *dev, int n_gpus
 extern "C" int hm_scan_condition(hm_scan *s, int ethresh, int do_trim, int do_symm, int64_t *nels_out)
 { int     G = s->ngpu, rc = HM_OK;
   int64_t n_new = -1;
+  if (s->invalid)
+    return hm_set_error(HM_EINVAL,"this scan was left unusable by an earlier failed conditioning");
   if (!do_trim && !do_symm)
     { if (nels_out) *nels_out = s->n;
       return HM_OK;
     }
-  for (int g = 0; g < G && rc == HM_OK; g++)
+  /* everything derived from the old table goes first: work buffers of both paths, the index */
+  s->ran = 0; s->have_direct = 0; s->have_symm = 0;
+  for (int g = 0; g < G; g++)
     { DevTable *D = s->d+g;
-      int64_t   n = s->n;
       HM_CUDA(cudaSetDevice(D->dev));
       HM_CUDA(cudaStreamSynchronize(D->st));
       dfree(D->dev,D->st,D->deg);    D->deg = NULL;
       dfree(D->dev,D->st,D->up);     D->up = NULL;
       dfree(D->dev,D->st,D->bucket); D->bucket = NULL;
       dfree(D->dev,D->st,D->filter); D->filter = NULL;
-      /* the table arrays are about to be replaced by plain cudaMalloc'ed ones: hand pooled ones back */
-      { PoolReg *R = g_pool + (D->dev < 64 ? D->dev : 0);
-        void *arr[3] = { D->keys, D->keys_lo, D->cnt };
-        for (int a = 0; a < 3; a++)
-          for (int k = 0; k < R->n; k++)
-            if (arr[a] != NULL && R->p[k] == arr[a])
-              { /* conditioning frees these with cudaFree, which is legal for pool memory */
-                R->p[k] = R->p[--R->n];
-              }
-      }
+      if (D->symm_work != NULL) { cudaFree(D->symm_work); D->symm_work = NULL; }
+      /* the table arrays are about to be replaced by plain cudaMalloc'ed ones: hand pooled ones back
+       * (conditioning frees them with cudaFree, which is legal for pool memory)                    */
+      PoolReg *R = g_pool + (D->dev < 64 ? D->dev : 0);
+      void *arr[3] = { D->keys, D->keys_lo, D->cnt };
+      for (int a = 0; a < 3; a++)
+        for (int k = 0; k < R->n; k++)
+          if (arr[a] != NULL && R->p[k] == arr[a])
+            R->p[k] = R->p[--R->n];
+    }
+  for (int g = 0; g < G && rc == HM_OK; g++)
+    { DevTable *D = s->d+g;
+      int64_t   n = s->n;
+      HM_CUDA(cudaSetDevice(D->dev));
       rc = hm_condition_arrays(s->kmer,ethresh,do_trim,do_symm,&D->keys,&D->keys_lo,&D->cnt,&n,D->st);
       s->launches += 6;
-      if (rc != HM_OK) return rc;
-      if (n_new >= 0 && n != n_new)
-        return hm_set_error(HM_ECUDA,"conditioning gave %lld entries on GPU %d but %lld on GPU 0",
-                            (long long) n,D->dev,(long long) n_new);
+      if (rc == HM_OK && n_new >= 0 && n != n_new)
+        rc = hm_set_error(HM_ECUDA,"conditioning gave %lld entries on GPU %d but %lld on GPU 0",
+                          (long long) n,D->dev,(long long) n_new);
+      if (rc != HM_OK && g > 0)
+        s->invalid = 1;                        /* the replicas no longer agree */
       n_new = n;
     }
-  s->n     = n_new;
-  s->bits  = hm_pick_bucket_bits(s->n);
-  s->fpos  = hm_pick_filter_bits(s->n);
-  s->idx64 = (s->n >= 0xFFFFFFF0ll);
+  if (rc == HM_OK)
+    { s->n     = n_new;
+      s->bits  = hm_pick_bucket_bits(s->n);
+      s->fpos  = hm_pick_filter_bits(s->n);
+      s->idx64 = (s->n >= 0xFFFFFFF0ll);
+    }
+  /* index (also after a failure on GPU 0: the old table is intact and stays usable) */
   size_t ib = s->idx64 ? 8 : 4;
-  for (int g = 0; g < G && rc == HM_OK; g++)
+  int    rc2 = HM_OK;
+  for (int g = 0; g < G && rc2 == HM_OK && !s->invalid; g++)
     { DevTable *D = s->d+g;
       int64_t   n = s->n;
       cudaError_t e;
       D->lo = n*g/G;
       D->hi = n*(g+1)/G;
-#define TRY(call) if (rc == HM_OK && (e = (call)) != cudaSuccess) rc = hm_cuda_fail(e,#call)
+#define TRY(call) if (rc2 == HM_OK && (e = (call)) != cudaSuccess) rc2 = hm_cuda_fail(e,#call)
       TRY(cudaSetDevice(D->dev));
-      TRY(dalloc(D->dev,D->st,(void **) &D->deg,(size_t) ((n+4)&~3ll)));
       TRY(dalloc(D->dev,D->st,(void **) &D->bucket,ib*(((size_t) 1<<s->bits)+1)));
-      TRY(dalloc(D->dev,D->st,(void **) &D->filter,sizeof(uint32_t)*(size_t) hm_filter_words(s->fpos)));
-      TRY(dalloc(D->dev,D->st,(void **) &D->up,ib*(size_t) (D->hi-D->lo+1)));
+      TRY(cudaMemsetAsync(D->fp_acc,0,4*sizeof(uint64_t),D->st));
 #undef TRY
-      if (rc == HM_OK)
-        rc = hm_k_build_bucket_index(D->keys,n,s->bits,D->bucket,s->idx64,D->st);
-      if (rc == HM_OK)
-        rc = hm_k_build_filter(D->keys,n,s->fpos,D->filter,D->st);
+      if (rc2 == HM_OK)
+        rc2 = hm_k_build_bucket_index(D->keys,n,s->bits,D->bucket,s->idx64,D->st);
+      if (rc2 == HM_OK && s->kmer >= HM_SYMM_MIN_KMER)
+        rc2 = hm_k_symm_fingerprint(D->keys,D->keys_lo,D->cnt,D->lo,D->hi,s->kmer,s->seed,D->fp_acc,D->st);
       s->launches += 2;
     }
   for (int g = 0; g < G; g++)
     { cudaSetDevice(s->d[g].dev);
       cudaError_t e = cudaStreamSynchronize(s->d[g].st);
-      if (rc == HM_OK && e != cudaSuccess) rc = hm_cuda_fail(e,"re-index after conditioning");
+      if (rc2 == HM_OK && e != cudaSuccess) rc2 = hm_cuda_fail(e,"re-index after conditioning");
     }
+  if (rc2 == HM_OK && !s->invalid)
+    rc2 = fingerprint_verdict(s);
+  if (rc2 != HM_OK)
+    s->invalid = 1;
   if (nels_out) *nels_out = s->n;
-  return rc;
+  return rc != HM_OK ? rc : rc2;
 }
 
 /* reverse complement of a left-aligned packed k-mer (k <= 32) */
@@ -545,10 +701,13 @@ extern "C" int hm_scan_examine(hm_scan *s, int ethresh, int *trim, int *symm)
   return rc;
 }
 
-extern "C" int hm_scan_run(hm_scan *s, int64_t *plot, hm_scan_stats *stats)
-{ double      t0 = now_ms();
-  int         G = s->ngpu, rc = HM_OK;
+/* the direct passes of hm_kernels.cu: any table */
+static int run_direct(hm_scan *s, int64_t *plot, hm_scan_stats *stats)
+{ int         G = s->ngpu, rc = HM_OK;
   int64_t     n = s->n, launches0 = s->launches;
+  if ((rc = ensure_direct(s)) != HM_OK)
+    return rc;
+  double      t0 = now_ms();
   cudaEvent_t ev[HM_MAX_GPUS][4];
   float       ms1 = 0, ms2 = 0, msall = 0;
 
@@ -654,10 +813,10 @@ extern "C" int hm_scan_run(hm_scan *s, int64_t *plot, hm_scan_stats *stats)
       for (int k = 0; k < 4; k++)
         cudaEventDestroy(ev[g][k]);
     }
-  s->ran = 1; s->peer_mode = peer_mode;
+  s->ran = 1; s->peer_mode = peer_mode; s->last_path = HM_PATH_DIRECT;
   if (stats != NULL)
     { stats->nels = n; stats->n_gpus = G; stats->bucket_bits = s->bits;
-      stats->filter_bits = s->fpos; stats->reserved = 0;
+      stats->filter_bits = s->fpos; stats->path = HM_PATH_DIRECT;
       stats->ms_h2d_unpack = s->ms_load;
       stats->ms_pass1 = ms1; stats->ms_pass2 = ms2;
       stats->ms_scan = G > 1 ? (t1-t0) : msall;
@@ -667,6 +826,153 @@ extern "C" int hm_scan_run(hm_scan *s, int64_t *plot, hm_scan_stats *stats)
     }
   (void) launches0;
   return HM_OK;
+}
+
+/* the strand-symmetric scan of hm_symm.cu: run scan -> (Bloom segments all-gathered over peer
+ * copies when >1 GPU) -> resolve -> plot reduce.  *status = the OR of the devices' status words:
+ * non-zero means the table was not symmetric after all and the plot must not be used.           */
+static int run_symm(hm_scan *s, int64_t *plot, hm_scan_stats *stats, uint64_t *status)
+{ int         G = s->ngpu, rc = HM_OK;
+  int64_t     n = s->n;
+  cudaEvent_t ev[HM_MAX_GPUS][4];
+  float       ms1 = 0, ms2 = 0, msall = 0;
+  if ((rc = ensure_symm(s)) != HM_OK)
+    return rc;
+  double      t0 = now_ms();
+  for (int g = 0; g < G; g++)
+    { DevTable *D = s->d+g;
+      HM_CUDA(cudaSetDevice(D->dev));
+      for (int k = 0; k < 4; k++)
+        HM_CUDA(cudaEventCreate(&ev[g][k]));
+      HM_CUDA(cudaEventRecord(ev[g][0],D->st));
+      HM_CUDA(cudaMemsetAsync(D->plot,0,sizeof(unsigned long long)*HM_PLOT_CELLS,D->st));
+      rc = hm_k_symm_runscan(D->keys,D->keys_lo,D->cnt,n,D->bucket,s->bits,s->idx64,s->kmer,D->slo,D->shi,
+                             D->symm_work,&D->symm_layout,G > 1 ? &s->ssh[g] : NULL,D->st);
+      if (rc != HM_OK) return rc;
+      s->launches += (D->shi > D->slo);
+      HM_CUDA(cudaEventRecord(ev[g][1],D->st));
+    }
+  if (G > 1)                                    /* every device pulls the other devices' Bloom segments */
+    { for (int g = 0; g < G; g++)
+        { HM_CUDA(cudaSetDevice(s->d[g].dev)); HM_CUDA(cudaStreamSynchronize(s->d[g].st)); }
+      for (int g = 0; g < G; g++)
+        { DevTable *D = s->d+g;
+          size_t    segb = sizeof(uint32_t)*(size_t) D->symm_layout.seg_words;
+          HM_CUDA(cudaSetDevice(D->dev));
+          for (int h = 0; h < G; h++)
+            if (h != g)
+              { DevTable *S = s->d+h;
+                HM_CUDA(cudaMemcpyPeerAsync((uint8_t *) D->symm_work + D->symm_layout.off_bloom + segb*h,D->dev,
+                                            (uint8_t *) S->symm_work + S->symm_layout.off_bloom + segb*h,S->dev,
+                                            segb,D->st));
+              }
+        }
+    }
+  for (int g = 0; g < G; g++)
+    { DevTable *D = s->d+g;
+      HM_CUDA(cudaSetDevice(D->dev));
+      HM_CUDA(cudaEventRecord(ev[g][2],D->st));
+      rc = hm_k_symm_resolve(D->keys,D->keys_lo,D->cnt,n,D->bucket,s->bits,s->idx64,s->kmer,
+                             D->symm_work,&D->symm_layout,G > 1 ? &s->ssh[g] : NULL,D->plot,D->st);
+      if (rc != HM_OK) return rc;
+      s->launches += 1;
+      HM_CUDA(cudaEventRecord(ev[g][3],D->st));
+    }
+  if (G > 1)
+    { unsigned long long *pl[HM_MAX_GPUS]; int dev[HM_MAX_GPUS]; cudaStream_t st[HM_MAX_GPUS];
+      for (int g = 0; g < G; g++)
+        { pl[g] = s->d[g].plot; dev[g] = s->d[g].dev; st[g] = s->d[g].st; }
+      rc = hm_peer_sum_plot(pl,dev,st,G);
+      if (rc != HM_OK) return rc;
+      s->launches += 1;
+    }
+  uint64_t hdr[HM_MAX_GPUS][2];
+  HM_CUDA(cudaSetDevice(s->d[0].dev));
+  HM_CUDA(cudaMemcpyAsync(plot,s->d[0].plot,sizeof(int64_t)*HM_PLOT_CELLS,
+                          cudaMemcpyDeviceToHost,s->d[0].st));
+  for (int g = 0; g < G; g++)
+    { DevTable *D = s->d+g;
+      HM_CUDA(cudaSetDevice(D->dev));
+      HM_CUDA(cudaMemcpyAsync(hdr[g],(uint8_t *) D->symm_work + D->symm_layout.off_header,2*sizeof(uint64_t),
+                              cudaMemcpyDeviceToHost,D->st));
+    }
+  for (int g = 0; g < G; g++)
+    { HM_CUDA(cudaSetDevice(s->d[g].dev));
+      HM_CUDA(cudaStreamSynchronize(s->d[g].st));
+    }
+  double t1 = now_ms();
+  *status = 0;
+  for (int g = 0; g < G; g++)
+    { float a = 0, b = 0, c = 0;
+      *status |= hdr[g][1];
+      cudaSetDevice(s->d[g].dev);
+      cudaEventElapsedTime(&a,ev[g][0],ev[g][1]);
+      cudaEventElapsedTime(&b,ev[g][2],ev[g][3]);
+      cudaEventElapsedTime(&c,ev[g][0],ev[g][3]);
+      if (a > ms1) ms1 = a;
+      if (b > ms2) ms2 = b;
+      if (c > msall) msall = c;
+      for (int k = 0; k < 4; k++)
+        cudaEventDestroy(ev[g][k]);
+    }
+  s->last_path = HM_PATH_SYMM;
+  if (stats != NULL)
+    { stats->nels = n; stats->n_gpus = G; stats->bucket_bits = s->bits;
+      stats->filter_bits = 0; stats->path = HM_PATH_SYMM;
+      stats->ms_h2d_unpack = s->ms_load;
+      stats->ms_pass1 = ms1; stats->ms_pass2 = ms2;
+      stats->ms_scan = G > 1 ? (t1-t0) : msall;
+      stats->ms_total = s->ms_load + (t1-t0);
+      stats->kernel_launches = s->launches;
+      stats->ms_alloc = s->ms_alloc; stats->ms_records = s->ms_records; stats->ms_index = s->ms_index;
+    }
+  return HM_OK;
+}
+
+extern "C" int hm_scan_is_symmetric(const hm_scan *s) { return s->symmetric; }
+
+extern "C" int hm_scan_run_path(hm_scan *s, int path, int64_t *plot, hm_scan_stats *stats)
+{ if (s->invalid)
+    return hm_set_error(HM_EINVAL,"this scan was left unusable by a failed conditioning");
+  if (path == HM_PATH_AUTO)
+    { const char *e = getenv("HETMERS_PATH");
+      if (e != NULL && strcmp(e,"direct") == 0) path = HM_PATH_DIRECT;
+      if (e != NULL && strcmp(e,"symm") == 0)   path = HM_PATH_SYMM;
+    }
+  if (path == HM_PATH_DIRECT || (path == HM_PATH_AUTO && !s->symmetric))
+    return run_direct(s,plot,stats);
+  if (path != HM_PATH_AUTO && path != HM_PATH_SYMM)
+    return hm_set_error(HM_EINVAL,"hm_scan_run_path: unknown path %d",path);
+  if (s->kmer < HM_SYMM_MIN_KMER || (path == HM_PATH_SYMM && !s->symmetric))
+    return hm_set_error(HM_EINVAL,"the table is not strand-symmetric (or k < %d): the symmetric scan "
+                                  "would not give the reference's answer",HM_SYMM_MIN_KMER);
+  uint64_t status = 0;
+  int rc = run_symm(s,plot,stats,&status);
+  if (rc != HM_OK)
+    return rc;
+  if (status == 0)
+    return HM_OK;
+  /* the fingerprint was fooled (2^-128) or a cut missed a run boundary: the direct passes are
+   * always right                                                                                */
+  if (path == HM_PATH_SYMM)
+    return hm_set_error(HM_EINVAL,"symmetric scan failed its own checks (status %llu)",(unsigned long long) status);
+  s->symmetric = 0;
+  return run_direct(s,plot,stats);
+}
+
+extern "C" int hm_scan_run(hm_scan *s, int64_t *plot, hm_scan_stats *stats)
+{ return hm_scan_run_path(s,HM_PATH_AUTO,plot,stats); }
+
+/* extract / download need the incidence array and the recorded partners of the direct passes */
+static int need_direct_results(hm_scan *s)
+{ if (s->ran)
+    return HM_OK;
+  int64_t *tmp = (int64_t *) malloc(sizeof(int64_t)*HM_PLOT_CELLS);
+  if (tmp == NULL)
+    return hm_set_error(HM_ENOMEM,"out of host memory");
+  int rc = run_direct(s,tmp,NULL);
+  free(tmp);
+  return rc;
 }
 
 static int rec_cmp(const void *a, const void *b)
@@ -682,8 +988,10 @@ static int rec_cmp(const void *a, const void *b)
  * recorded partners of a preceding hm_scan_run.  Two launches per GPU: count, then fill.        */
 extern "C" int hm_scan_extract(hm_scan *s, const uint16_t *pixmap, hm_pair_rec **out, int64_t *n_out)
 { int G = s->ngpu, rc = HM_OK;
-  if (!s->ran)
-    return hm_set_error(HM_EINVAL,"hm_scan_extract needs a preceding hm_scan_run");
+  if (s->invalid)
+    return hm_set_error(HM_EINVAL,"this scan was left unusable by a failed conditioning");
+  if ((rc = need_direct_results(s)) != HM_OK)
+    return rc;
   int64_t      total = 0, cnts[HM_MAX_GPUS];
   hm_pair_rec *d_out[HM_MAX_GPUS];
   uint16_t    *d_pix[HM_MAX_GPUS];
@@ -757,6 +1065,10 @@ extern "C" int hm_scan_download(hm_scan *s, uint64_t *keys, uint64_t *keys_lo, u
   if (cnt != NULL)
     HM_CUDA(cudaMemcpy(cnt,D->cnt,sizeof(uint16_t)*(size_t) s->n,cudaMemcpyDeviceToHost));
   if (deg != NULL)                      /* every owner's slice (identical copies in dense mode) */
+    { int rc = need_direct_results(s);  /* (the symmetric scan never materialises the array) */
+      if (rc != HM_OK) return rc;
+    }
+  if (deg != NULL)
     for (int g = 0; g < s->ngpu; g++)
       { DevTable *O = s->d+g;
         HM_CUDA(cudaSetDevice(O->dev));

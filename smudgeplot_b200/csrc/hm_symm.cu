@@ -1,0 +1,600 @@
+/*******************************************************************************************
+ * hm_symm.cu -- the strand-symmetric scan: every table entry is read ONCE.
+ *
+ * The reference insists on a table that holds the reverse complement of each of its k-mers with
+ * the same count (examine_table, PloidyPlot.c:1199-1229; it runs `Symmex` otherwise, :1401-1414),
+ * but then searches all k positions directly.  On a table that really is symmetric the pairs that
+ * differ at a LOW position p < Pr = k/2 are the mirror images (u,v) -> (rc v, rc u) of the pairs
+ * that differ at the HIGH position k-1-p, and pairs at high positions sit next to each other in the
+ * sorted table: both members share their first Pr bases, i.e. lie in one short *run* of entries.
+ * So with N_p(x) = number of partners of x at position p (count sum <= SMAX, PloidyPlot.c:259):
+ *
+ *     deg(x) = H(x) + U(rc x),   H(x) = sum_{p >= Pr}   N_p(x)     (found inside x's run)
+ *                                U(x) = sum_{p >= k-Pr} N_p(x)     (ditto; = H without the middle
+ *                                                                   base of an odd k)
+ *     deg(rc x) = deg(x), and a pair and its mirror image land in the same plot cell.
+ *
+ *   symm_fingerprint_kernel   is the table symmetric?  Keyed multiset fingerprints of
+ *                             {(x,cnt)} and {(rc x,cnt)} (seeds drawn per process); equal sums
+ *                             <=> equal multisets up to a 2^-128 chance.  Tables that fail --
+ *                             they may still pass the reference's one-k-mer probe -- take the
+ *                             direct search of hm_kernels.cu, so the answer is the reference's
+ *                             either way.
+ *   runscan_kernel            ("pass 1") tiles of the sorted table are staged into shared memory by
+ *                             TMA bulk copies; every entry scans its run: H, U, its partner.
+ *                             Entries with U > 0 (the set S) are added to a Bloom filter; pairs
+ *                             (x < y) with H(x) = H(y) = 1 become candidate records.
+ *   resolve_kernel            ("pass 2") a candidate is an isolated pair iff neither rc x nor rc y
+ *                             is in S: Bloom look-up (L2 resident), hits confirmed exactly by
+ *                             scanning the run of rc x in the table.  Isolated pairs are counted
+ *                             into the plot (shared-memory tile + 64-bit atomics), twice when the
+ *                             mirror image is a different pair (PloidyPlot.c:401-415 sees both).
+ *
+ * Replaces analysis_in_core_1/_2 + the recursion around them (PloidyPlot.c:454-700,:851-1084)
+ * for symmetric tables.  Traffic: keys + counts once (TBYTE per entry) + ~2 B per entry of
+ * candidate records, instead of 2 x k merge levels in the reference.
+ *******************************************************************************************/
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "hetmers_b200.h"
+#include "hm_internal.h"
+#include "hm_device.cuh"
+
+#define RS_THREADS 256
+#define RS_EPT     8
+#define RS_TILE    (RS_THREADS*RS_EPT)        /* entries per CTA tile                            */
+#define RS_HALO    64                          /* entries staged on either side of the tile      */
+#define RS_WIN     (RS_TILE+2*RS_HALO)
+#define RS_SCANCAP RS_HALO                     /* longest run half scanned linearly               */
+
+#define SY_STATUS_ASYMMETRIC 1ull              /* a reverse complement was not in the table      */
+#define SY_STATUS_OVERFLOW   2ull              /* candidate list full                             */
+
+/* device view of the work area (hm_symm_layout) */
+struct SymmView
+  { unsigned long long *cand_n;
+    unsigned long long *status;
+    uint32_t *bloom;                            /* n_seg segments of seg_words words               */
+    uint32_t  seg_words;
+    int       n_seg, self;
+    uint64_t  first_key[HM_MAX_SHARDS];         /* word 0 of the first key of segments 1.. (0 unused) */
+    uint64_t *cand_key, *cand_lo, *cand_meta;
+    unsigned long long cand_cap;
+  };
+
+/* Bloom position of key (hi,lo): one bit in one 32-bit word of the owner's segment */
+template <int KW>
+__device__ __forceinline__ void bloom_slot(const SymmView &W, int seg, uint64_t hi, uint64_t lo,
+                                           uint32_t *&word, uint32_t &bit)
+{ uint64_t v = hi;
+  if (KW == 2) v ^= lo * 0xD6E8FEB86659FD93ull;
+  uint64_t m = v * 0x9E3779B97F4A7C15ull;
+  uint32_t h = (uint32_t) (m >> 32);
+  word = W.bloom + (size_t) seg * W.seg_words + __umulhi(h,W.seg_words);
+  bit  = 1u << ((uint32_t) (m >> 27) & 31);
+}
+
+__device__ __forceinline__ int owner_of(const SymmView &W, uint64_t hi)
+{ int r = 0;
+  for (int s = 1; s < W.n_seg; s++)
+    r += (hi >= W.first_key[s]);
+  return r;
+}
+
+/* all partners of x at positions >= p0, one bucket look-up per candidate (long runs only) */
+template <typename IdxT, int KW>
+__device__ __noinline__ void neighbours_slow(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ keys_lo,
+                                             const uint16_t *__restrict__ cnt, const IdxT *__restrict__ bucket,
+                                             int bshift, int kmer, int p0, int pup,
+                                             uint64_t x, uint64_t xl, int cx,
+                                             int &H, int &U, int64_t &part, int &ppos)
+{ H = 0; U = 0; part = -1; ppos = 0;
+  for (int p = p0; p < kmer; p++)
+    { int b = base_at<KW>(x,xl,p);
+      for (int c = 0; c < 4; c++)
+        { if (c == b) continue;
+          uint64_t y = x, yl = xl;
+          set_base<KW>(y,yl,p,c);
+          int64_t j = bucket_find<IdxT,KW>(keys,keys_lo,bucket,bshift,y,yl);
+          if (j >= 0 && cx + (int) __ldg(cnt+j) <= HM_SMAX)
+            { H += 1;
+              if (p >= pup) U += 1;
+              part = j; ppos = p;
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------- fingerprint -------- */
+
+__device__ __forceinline__ uint64_t fp_mix(uint64_t hi, uint64_t lo, uint32_t c, uint64_t seed)
+{ uint64_t v = (hi ^ seed) * 0xBF58476D1CE4E5B9ull;
+  v ^= v >> 32;
+  v = (v + lo + ((uint64_t) c << 40) + c) * 0x94D049BB133111EBull;
+  v ^= v >> 29;
+  v *= (seed | 1);
+  v ^= v >> 32;
+  return v;
+}
+
+template <int KW>
+__global__ void __launch_bounds__(256)
+symm_fingerprint_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ keys_lo,
+                        const uint16_t *__restrict__ cnt, int64_t i0, int64_t i1, int kmer,
+                        uint64_t seed0, uint64_t seed1, unsigned long long *__restrict__ acc)
+{ uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t i = i0 + (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += stride)
+    { uint64_t x = keys[i], xl = KW == 2 ? keys_lo[i] : 0, r, rl;
+      uint32_t c = cnt[i];
+      revcomp_kmer<KW>(x,xl,kmer,r,rl);
+      a0 += fp_mix(x,xl,c,seed0);  a1 += fp_mix(x,xl,c,seed1);
+      a2 += fp_mix(r,rl,c,seed0);  a3 += fp_mix(r,rl,c,seed1);
+    }
+  for (int o = 16; o > 0; o >>= 1)
+    { a0 += __shfl_xor_sync(0xffffffffu,a0,o); a1 += __shfl_xor_sync(0xffffffffu,a1,o);
+      a2 += __shfl_xor_sync(0xffffffffu,a2,o); a3 += __shfl_xor_sync(0xffffffffu,a3,o);
+    }
+  if ((threadIdx.x & 31) == 0)
+    { atomicAdd(acc+0,(unsigned long long) a0); atomicAdd(acc+1,(unsigned long long) a1);
+      atomicAdd(acc+2,(unsigned long long) a2); atomicAdd(acc+3,(unsigned long long) a3);
+    }
+}
+
+extern "C" int hm_k_symm_fingerprint(const uint64_t *d_keys, const uint64_t *d_keys_lo, const uint16_t *d_cnt,
+                                     int64_t i0, int64_t i1, int kmer, const uint64_t seed[2],
+                                     uint64_t *d_acc, void *stream)
+{ if (kmer < 1 || kmer > HM_MAX_KMER || (kmer > 32) != (d_keys_lo != NULL) || seed == NULL || d_acc == NULL)
+    return hm_set_error(HM_EINVAL,"symm_fingerprint: bad arguments (k=%d)",kmer);
+  if (i1 <= i0)
+    return HM_OK;
+  int64_t want = (i1-i0+255)/256;
+  int     grid = (int) (want < 148*16 ? want : 148*16);
+  if (kmer <= 32)
+    symm_fingerprint_kernel<1><<<grid,256,0,(cudaStream_t) stream>>>
+        (d_keys,NULL,d_cnt,i0,i1,kmer,seed[0],seed[1],(unsigned long long *) d_acc);
+  else
+    symm_fingerprint_kernel<2><<<grid,256,0,(cudaStream_t) stream>>>
+        (d_keys,d_keys_lo,d_cnt,i0,i1,kmer,seed[0],seed[1],(unsigned long long *) d_acc);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return hm_cuda_fail(e,"symm_fingerprint_kernel");
+  return HM_OK;
+}
+
+/* per-process seeds of the fingerprint (the table cannot have been chosen against them) */
+extern "C" void hm_symm_seeds(uint64_t seed[2])
+{ static uint64_t s[2] = {0,0};
+  static int have = 0;
+  if (!have)
+    { FILE *f = fopen("/dev/urandom","rb");
+      if (f == NULL || fread(s,sizeof(uint64_t),2,f) != 2)
+        { struct timespec ts;
+          clock_gettime(CLOCK_REALTIME,&ts);
+          s[0] = 0x9E3779B97F4A7C15ull * (uint64_t) ts.tv_nsec ^ (uint64_t) ts.tv_sec;
+          s[1] = 0xD1B54A32D192ED03ull * (uint64_t) (uintptr_t) &ts ^ ((uint64_t) ts.tv_nsec << 17);
+        }
+      if (f != NULL) fclose(f);
+      have = 1;
+    }
+  seed[0] = s[0]; seed[1] = s[1];
+}
+
+/* ------------------------------------------------------------------------ layout -------- */
+
+extern "C" int hm_symm_plan(int64_t n, int64_t range, int kmer, int n_seg, hm_symm_layout *out)
+{ if (out == NULL || n < 0 || range < 0 || range > n || n_seg < 1 || n_seg > HM_MAX_SHARDS)
+    return hm_set_error(HM_EINVAL,"hm_symm_plan: bad arguments");
+  int bits = 2;                                  /* Bloom bits per table entry (S is ~1/6 of the table) */
+  const char *e = getenv("HETMERS_BLOOM_BITS");
+  if (e != NULL && atoi(e) >= 1 && atoi(e) <= 64)
+    bits = atoi(e);
+  int64_t per = (n+n_seg-1)/n_seg;               /* every segment the same size on every rank: all-gather friendly */
+  int64_t segw = (per*bits+31)/32;
+  if (segw < 1024) segw = 1024;
+  segw = (segw+63) & ~63ll;
+  if (segw > 0x7fffffffll)
+    return hm_set_error(HM_EUNSUPPORTED,"Bloom segment of %lld words too large",(long long) segw);
+  int64_t cap = range/2 + 1024;
+  int64_t at = 0;
+  memset(out,0,sizeof(*out));
+  out->off_header = at;  at += 256;
+  out->off_bloom = at;   at += 4*segw*n_seg;
+  out->seg_words = segw;
+  at = (at+255) & ~255ll;
+  out->off_cand_key = at;   at += 8*cap;
+  out->off_cand_lo = at;    at += (kmer > 32) ? 8*cap : 0;
+  out->off_cand_meta = at;  at += 8*cap;
+  out->cand_cap = cap;
+  out->n_seg = n_seg;
+  out->range = range;
+  out->bytes = (at+255) & ~255ll;
+  return HM_OK;
+}
+
+static SymmView make_view(void *d_work, const hm_symm_layout *L, const hm_symm_shards *sh)
+{ SymmView W;
+  uint8_t *b = (uint8_t *) d_work;
+  memset(&W,0,sizeof(W));
+  W.cand_n    = (unsigned long long *) (b + L->off_header);
+  W.status    = W.cand_n + 1;
+  W.bloom     = (uint32_t *) (b + L->off_bloom);
+  W.seg_words = (uint32_t) L->seg_words;
+  W.n_seg     = L->n_seg;
+  W.self      = 0;
+  if (sh != NULL && sh->n_seg > 1)
+    { W.self = sh->self;
+      for (int r = 0; r < sh->n_seg; r++) W.first_key[r] = sh->first_key[r];
+    }
+  W.cand_key  = (uint64_t *) (b + L->off_cand_key);
+  W.cand_lo   = (uint64_t *) (b + L->off_cand_lo);
+  W.cand_meta = (uint64_t *) (b + L->off_cand_meta);
+  W.cand_cap  = (unsigned long long) L->cand_cap;
+  return W;
+}
+
+/* ------------------------------------------------------------------------ pass 1 -------- */
+
+template <typename IdxT, int KW>
+__global__ void __launch_bounds__(RS_THREADS)
+runscan_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ keys_lo,
+               const uint16_t *__restrict__ cnt, int64_t n, const IdxT *__restrict__ bucket, int bshift,
+               int kmer, int64_t lo, int64_t hi, int64_t tile0, int use_tma, const SymmView W)
+{ extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t s_bar;
+  uint64_t *s_key = (uint64_t *) smem;
+  uint64_t *s_klo = s_key + (KW == 2 ? RS_WIN : 0);
+  uint16_t *s_cnt = (uint16_t *) (s_key + KW*RS_WIN);
+
+  const int      Pr   = kmer >> 1;                 /* run = entries sharing their first Pr bases     */
+  const int      pup  = kmer - Pr;                 /* positions >= pup have a mirror position < Pr   */
+  const int      psh  = 64-2*Pr;
+  const unsigned FULL = 0xffffffffu;
+  const int      lane = threadIdx.x & 31;
+  const unsigned lt   = (1u << lane) - 1;
+
+  const int64_t T0 = (tile0 + blockIdx.x) * RS_TILE;
+  const int64_t ws = T0 - RS_HALO;
+  const int64_t e0 = ws > 0 ? ws : 0;
+  const int64_t e1 = T0+RS_TILE+RS_HALO < n ? T0+RS_TILE+RS_HALO : n;
+  const int     v0 = (int) (e0-ws), v1 = (int) (e1-ws);          /* valid window slots [v0,v1)   */
+
+  /* ---- stage the window: TMA bulk copies for the 16-byte multiple, plain loads for the rest ---- */
+  const int m   = v1-v0;
+  const int mt  = use_tma ? (m & ~7) : 0;
+  if (threadIdx.x == 0 && mt > 0)
+    { mbar_init(&s_bar,1);
+      fence_proxy_async_smem();
+    }
+  __syncthreads();
+  if (threadIdx.x == 0 && mt > 0)
+    { mbar_arrive_expect_tx(&s_bar,(unsigned) (mt*(8*KW+2)));
+      bulk_copy_g2s(s_key+v0,keys+e0,(unsigned) (8*mt),&s_bar);
+      if (KW == 2)
+        bulk_copy_g2s(s_klo+v0,keys_lo+e0,(unsigned) (8*mt),&s_bar);
+      bulk_copy_g2s(s_cnt+v0,cnt+e0,(unsigned) (2*mt),&s_bar);
+    }
+  for (int j = mt + threadIdx.x; j < m; j += RS_THREADS)
+    { s_key[v0+j] = keys[e0+j];
+      if (KW == 2) s_klo[v0+j] = keys_lo[e0+j];
+      s_cnt[v0+j] = cnt[e0+j];
+    }
+  __syncthreads();
+  if (mt > 0)
+    mbar_wait(&s_bar,0);
+
+#pragma unroll 1
+  for (int e = 0; e < RS_EPT; e++)
+    { const int     t = threadIdx.x + e*RS_THREADS;
+      const int     w = t + RS_HALO;
+      const int64_t g = T0+t;
+      const bool    active = (g >= lo && g < hi);
+      bool     emit = false, insert = false;
+      uint64_t x = 0, xl = 0, meta = 0;
+      if (active)
+        { x = s_key[w];
+          if (KW == 2) xl = s_klo[w];
+          const int cx = s_cnt[w];
+          int  H = 0, U = 0, pj = -1, ppos = 0;
+          bool ovf = false;
+          int  b0, b1, j;
+          /* backward half of the run */
+          { int lim = w-RS_SCANCAP > v0 ? w-RS_SCANCAP : v0;
+            for (j = w-1; j >= lim; j--)
+              { uint64_t z = s_key[j];
+                if (((z ^ x) >> psh) != 0) break;
+                int pos;
+                if (one_base_apart<KW>(x,xl,z,KW == 2 ? s_klo[j] : 0,pos) && cx + (int) s_cnt[j] <= HM_SMAX)
+                  { H += 1; U += (pos >= pup); pj = j; ppos = pos; }
+              }
+            if (j < lim && !(lim == v0 && e0 == 0)) ovf = true;     /* run longer than the window */
+            b0 = j+1;
+          }
+          /* forward half */
+          { int lim = w+RS_SCANCAP < v1-1 ? w+RS_SCANCAP : v1-1;
+            for (j = w+1; j <= lim; j++)
+              { uint64_t z = s_key[j];
+                if (((z ^ x) >> psh) != 0) break;
+                int pos;
+                if (one_base_apart<KW>(x,xl,z,KW == 2 ? s_klo[j] : 0,pos) && cx + (int) s_cnt[j] <= HM_SMAX)
+                  { H += 1; U += (pos >= pup); pj = j; ppos = pos; }
+              }
+            if (j > lim && !(lim == v1-1 && e1 == n)) ovf = true;
+            b1 = j;
+          }
+          if (!ovf)
+            { insert = (U > 0);
+              if (H == 1 && pj > w)                      /* x is the lower member: is y's only partner x? */
+                { uint64_t y = s_key[pj], yl = KW == 2 ? s_klo[pj] : 0;
+                  const int cy = s_cnt[pj];
+                  int Hy = 0;
+                  for (j = b0; j < b1 && Hy < 2; j++)
+                    { if (j == pj) continue;
+                      int pos;
+                      if (one_base_apart<KW>(y,yl,s_key[j],KW == 2 ? s_klo[j] : 0,pos) &&
+                          cy + (int) s_cnt[j] <= HM_SMAX)
+                        Hy += 1;
+                    }
+                  if (Hy == 1)
+                    { emit = true;
+                      meta = (uint64_t) cx | ((uint64_t) cy << 16) | ((uint64_t) ppos << 32) |
+                             ((uint64_t) base_at<KW>(y,yl,ppos) << 40);
+                    }
+                }
+            }
+          else
+            { int64_t part;
+              neighbours_slow<IdxT,KW>(keys,keys_lo,cnt,bucket,bshift,kmer,Pr,pup,x,xl,cx,H,U,part,ppos);
+              insert = (U > 0);
+              if (H == 1 && part > g)
+                { uint64_t y = __ldg(keys+part), yl = KW == 2 ? __ldg(keys_lo+part) : 0;
+                  const int cy = __ldg(cnt+part);
+                  int Hy, Uy, py; int64_t party;
+                  neighbours_slow<IdxT,KW>(keys,keys_lo,cnt,bucket,bshift,kmer,Pr,pup,y,yl,cy,Hy,Uy,party,py);
+                  if (Hy == 1)
+                    { emit = true;
+                      meta = (uint64_t) cx | ((uint64_t) cy << 16) | ((uint64_t) ppos << 32) |
+                             ((uint64_t) base_at<KW>(y,yl,ppos) << 40);
+                    }
+                }
+            }
+        }
+      if (insert)
+        { uint32_t *word, bit;
+          bloom_slot<KW>(W,W.self,x,xl,word,bit);
+          atomicOr(word,bit);
+        }
+      const unsigned bal = __ballot_sync(FULL,emit);
+      if (bal != 0)
+        { unsigned long long base = 0;
+          if (lane == 0)
+            base = atomicAdd(W.cand_n,(unsigned long long) __popc(bal));
+          base = __shfl_sync(FULL,base,0);
+          if (emit)
+            { unsigned long long at = base + __popc(bal & lt);
+              if (at < W.cand_cap)
+                { W.cand_key[at] = x;
+                  if (KW == 2) W.cand_lo[at] = xl;
+                  W.cand_meta[at] = meta;
+                }
+              else
+                atomicOr(W.status,SY_STATUS_OVERFLOW);
+            }
+        }
+    }
+}
+
+template <typename IdxT, int KW>
+static cudaError_t launch_runscan(const uint64_t *keys, const uint64_t *keys_lo, const uint16_t *cnt, int64_t n,
+                                  const void *bucket, int bits, int kmer, int64_t lo, int64_t hi,
+                                  const SymmView &W, cudaStream_t st)
+{ size_t smem = (size_t) RS_WIN*(8*KW+2);                    /* 21.8 / 39.2 KB: below the 48 KB default */
+  int64_t tile0 = lo/RS_TILE, tile1 = (hi+RS_TILE-1)/RS_TILE;
+  int     tma   = ((((uintptr_t) keys) | ((uintptr_t) cnt) | ((uintptr_t) (keys_lo ? keys_lo : keys))) & 15) == 0;
+  runscan_kernel<IdxT,KW><<<(unsigned) (tile1-tile0),RS_THREADS,smem,st>>>
+      (keys,keys_lo,cnt,n,(const IdxT *) bucket,64-bits,kmer,lo,hi,tile0,tma,W);
+  return cudaGetLastError();
+}
+
+extern "C" int hm_k_symm_runscan(const uint64_t *d_keys, const uint64_t *d_keys_lo, const uint16_t *d_cnt, int64_t n,
+                                 const void *d_bucket, int bits, int idx64, int kmer, int64_t lo, int64_t hi,
+                                 void *d_work, const hm_symm_layout *layout, const hm_symm_shards *shards,
+                                 void *stream)
+{ if (kmer < HM_SYMM_MIN_KMER || kmer > HM_MAX_KMER)
+    return hm_set_error(HM_EUNSUPPORTED,"symmetric scan needs %d <= k <= %d (k=%d)",HM_SYMM_MIN_KMER,HM_MAX_KMER,kmer);
+  if (lo < 0 || hi > n || lo > hi || bits < 1 || bits > 30 || d_work == NULL || layout == NULL)
+    return hm_set_error(HM_EINVAL,"symm_runscan: bad range [%lld,%lld) of %lld or bits %d",
+                        (long long) lo,(long long) hi,(long long) n,bits);
+  if ((kmer > 32) != (d_keys_lo != NULL))
+    return hm_set_error(HM_EINVAL,"symm_runscan: second key word array %s for k=%d",
+                        d_keys_lo ? "given" : "missing",kmer);
+  if ((shards != NULL && shards->n_seg > 1) != (layout->n_seg > 1) ||
+      (shards != NULL && shards->n_seg > 1 && (shards->n_seg != layout->n_seg || shards->self < 0 ||
+                                               shards->self >= shards->n_seg)))
+    return hm_set_error(HM_EINVAL,"symm_runscan: shard table does not match the work-area layout");
+  cudaStream_t st = (cudaStream_t) stream;
+  SymmView W = make_view(d_work,layout,shards);
+  HM_CUDA(cudaMemsetAsync(W.cand_n,0,256,st));
+  HM_CUDA(cudaMemsetAsync(W.bloom + (size_t) W.self*W.seg_words,0,sizeof(uint32_t)*(size_t) W.seg_words,st));
+  if (hi == lo)
+    return HM_OK;
+  cudaError_t e;
+  if (kmer <= 32)
+    e = idx64 ? launch_runscan<uint64_t,1>(d_keys,NULL,d_cnt,n,d_bucket,bits,kmer,lo,hi,W,st)
+              : launch_runscan<uint32_t,1>(d_keys,NULL,d_cnt,n,d_bucket,bits,kmer,lo,hi,W,st);
+  else
+    e = idx64 ? launch_runscan<uint64_t,2>(d_keys,d_keys_lo,d_cnt,n,d_bucket,bits,kmer,lo,hi,W,st)
+              : launch_runscan<uint32_t,2>(d_keys,d_keys_lo,d_cnt,n,d_bucket,bits,kmer,lo,hi,W,st);
+  if (e != cudaSuccess)
+    return hm_cuda_fail(e,"runscan_kernel");
+  return HM_OK;
+}
+
+/* ------------------------------------------------------------------------ pass 2 -------- */
+
+#define RV_TS 192      /* shared-memory plot tile: sums < 192, mins < 96 (72 KB) */
+#define RV_TM 96
+#define RV_THREADS 512
+#define RV_CTAS_PER_SM 3
+
+/* does table entry q have a partner at a position >= pup?  (exact; q must be in the table) */
+template <typename IdxT, int KW>
+__device__ __noinline__ bool has_upper_partner(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ keys_lo,
+                                               const uint16_t *__restrict__ cnt, int64_t n,
+                                               const IdxT *__restrict__ bucket, int bshift, int kmer,
+                                               uint64_t q, uint64_t ql, unsigned long long *status)
+{ const int Pr = kmer >> 1, pup = kmer-Pr, psh = 64-2*Pr;
+  int64_t j = bucket_find<IdxT,KW>(keys,keys_lo,bucket,bshift,q,ql);
+  if (j < 0)
+    { atomicOr(status,SY_STATUS_ASYMMETRIC);
+      return true;
+    }
+  const int cq = __ldg(cnt+j);
+  bool capped = false;
+  for (int dir = -1; dir <= 1; dir += 2)
+    { int steps = 0;
+      for (int64_t i = j+dir; i >= 0 && i < n; i += dir)
+        { uint64_t z = __ldg(keys+i);
+          if (((z ^ q) >> psh) != 0) break;
+          if (++steps > RS_SCANCAP) { capped = true; break; }
+          int pos;
+          if (one_base_apart<KW>(q,ql,z,KW == 2 ? __ldg(keys_lo+i) : 0,pos) && pos >= pup &&
+              cq + (int) __ldg(cnt+i) <= HM_SMAX)
+            return true;
+        }
+    }
+  if (!capped)
+    return false;
+  int H, U, ppos; int64_t part;
+  neighbours_slow<IdxT,KW>(keys,keys_lo,cnt,bucket,bshift,kmer,pup,pup,q,ql,cq,H,U,part,ppos);
+  return (U > 0);
+}
+
+template <typename IdxT, int KW>
+__global__ void __launch_bounds__(RV_THREADS,RV_CTAS_PER_SM)
+resolve_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ keys_lo,
+               const uint16_t *__restrict__ cnt, int64_t n, const IdxT *__restrict__ bucket, int bshift,
+               int kmer, const SymmView W, unsigned long long *__restrict__ plot)
+{ extern __shared__ uint32_t tile[];
+  for (int t = threadIdx.x; t < RV_TS*RV_TM; t += blockDim.x)
+    tile[t] = 0;
+  __syncthreads();
+  unsigned long long nc = *W.cand_n;
+  if (nc > W.cand_cap) nc = W.cand_cap;
+  const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t) nc; i += stride)
+    { const uint64_t x = W.cand_key[i], xl = KW == 2 ? W.cand_lo[i] : 0, meta = W.cand_meta[i];
+      const int cx = (int) (meta & 0xffff), cy = (int) ((meta >> 16) & 0xffff);
+      const int p  = (int) ((meta >> 32) & 0xff), yb = (int) ((meta >> 40) & 3);
+      uint64_t rx, rxl, ry, ryl;
+      revcomp_kmer<KW>(x,xl,kmer,rx,rxl);
+      ry = rx; ryl = rxl;
+      set_base<KW>(ry,ryl,kmer-1-p,3-yb);                    /* rc y = rc x with the mirrored base swapped */
+      uint32_t *wa, *wb, ba, bb;
+      bloom_slot<KW>(W,W.n_seg > 1 ? owner_of(W,rx) : 0,rx,rxl,wa,ba);
+      bloom_slot<KW>(W,W.n_seg > 1 ? owner_of(W,ry) : 0,ry,ryl,wb,bb);
+      const uint32_t va = __ldg(wa), vb = __ldg(wb);
+      bool taint = false;
+      if ((va & ba) != 0)
+        taint = has_upper_partner<IdxT,KW>(keys,keys_lo,cnt,n,bucket,bshift,kmer,rx,rxl,W.status);
+      if (!taint && (vb & bb) != 0)
+        taint = has_upper_partner<IdxT,KW>(keys,keys_lo,cnt,n,bucket,bshift,kmer,ry,ryl,W.status);
+      if (taint)
+        continue;
+      const unsigned wgt = (2*p == kmer-1) ? 1u : 2u;          /* middle base: the mirror pair is found itself */
+      const int s = cx+cy;
+      const int m = cx < cy ? cx : cy;
+      if (s < RV_TS && m < RV_TM)
+        atomicAdd(tile + s*RV_TM + m, wgt);
+      else
+        atomicAdd(plot + s*HM_PLOT_W + m, (unsigned long long) wgt);
+    }
+  __syncthreads();
+  for (int t = threadIdx.x; t < RV_TS*RV_TM; t += blockDim.x)
+    { uint32_t v = tile[t];
+      if (v != 0)
+        atomicAdd(plot + (t/RV_TM)*HM_PLOT_W + (t%RV_TM), (unsigned long long) v);
+    }
+}
+
+template <typename IdxT, int KW>
+static cudaError_t launch_resolve(const uint64_t *keys, const uint64_t *keys_lo, const uint16_t *cnt, int64_t n,
+                                  const void *bucket, int bits, int kmer, const SymmView &W,
+                                  unsigned long long *plot, int64_t range, cudaStream_t st)
+{ static int configured[64] = {0};                            /* per instantiation */
+  size_t smem = (size_t) RV_TS*RV_TM*sizeof(uint32_t);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (dev >= 64 || !configured[dev])
+    { cudaError_t e = cudaFuncSetAttribute(resolve_kernel<IdxT,KW>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem);
+      if (e != cudaSuccess) return e;
+      if (dev < 64) configured[dev] = 1;
+    }
+  cudaDeviceGetAttribute(&sms,cudaDevAttrMultiProcessorCount,dev);
+  int64_t want = (range/8+RV_THREADS-1)/RV_THREADS;            /* ~1 candidate per 10 entries */
+  int     grid = (int) (want < sms*RV_CTAS_PER_SM ? (want > 0 ? want : 1) : sms*RV_CTAS_PER_SM);
+  resolve_kernel<IdxT,KW><<<grid,RV_THREADS,smem,st>>>(keys,keys_lo,cnt,n,(const IdxT *) bucket,64-bits,kmer,W,plot);
+  return cudaGetLastError();
+}
+
+extern "C" int hm_k_symm_resolve(const uint64_t *d_keys, const uint64_t *d_keys_lo, const uint16_t *d_cnt, int64_t n,
+                                 const void *d_bucket, int bits, int idx64, int kmer,
+                                 void *d_work, const hm_symm_layout *layout, const hm_symm_shards *shards,
+                                 unsigned long long *d_plot, void *stream)
+{ if (kmer < HM_SYMM_MIN_KMER || kmer > HM_MAX_KMER || d_work == NULL || layout == NULL || d_plot == NULL)
+    return hm_set_error(HM_EINVAL,"symm_resolve: bad arguments");
+  if ((kmer > 32) != (d_keys_lo != NULL))
+    return hm_set_error(HM_EINVAL,"symm_resolve: second key word array %s for k=%d",
+                        d_keys_lo ? "given" : "missing",kmer);
+  cudaStream_t st = (cudaStream_t) stream;
+  SymmView W = make_view(d_work,layout,shards);
+  int64_t range = layout->range;
+  cudaError_t e;
+  if (kmer <= 32)
+    e = idx64 ? launch_resolve<uint64_t,1>(d_keys,NULL,d_cnt,n,d_bucket,bits,kmer,W,d_plot,range,st)
+              : launch_resolve<uint32_t,1>(d_keys,NULL,d_cnt,n,d_bucket,bits,kmer,W,d_plot,range,st);
+  else
+    e = idx64 ? launch_resolve<uint64_t,2>(d_keys,d_keys_lo,d_cnt,n,d_bucket,bits,kmer,W,d_plot,range,st)
+              : launch_resolve<uint32_t,2>(d_keys,d_keys_lo,d_cnt,n,d_bucket,bits,kmer,W,d_plot,range,st);
+  if (e != cudaSuccess)
+    return hm_cuda_fail(e,"resolve_kernel");
+  return HM_OK;
+}
+
+/* candidate count + status word of the last runscan/resolve on this work area (synchronises) */
+extern "C" int hm_symm_status(const void *d_work, const hm_symm_layout *layout, uint64_t *n_cand,
+                              uint64_t *status, void *stream)
+{ uint64_t h[2] = {0,0};
+  HM_CUDA(cudaMemcpyAsync(h,(const uint8_t *) d_work + layout->off_header,sizeof(h),cudaMemcpyDeviceToHost,
+                          (cudaStream_t) stream));
+  HM_CUDA(cudaStreamSynchronize((cudaStream_t) stream));
+  if (n_cand != NULL) *n_cand = h[0];
+  if (status != NULL) *status = h[1];
+  return HM_OK;
+}
+
+/* Move a proposed shard cut to the next run boundary at or after it (a run = entries sharing their
+ * first k/2 bases): pairs found by the run scan then never straddle two shards.                 */
+extern "C" int hm_symm_align_cut(const uint64_t *d_keys, int64_t n, int kmer, int64_t cut, int64_t *out)
+{ if (d_keys == NULL || out == NULL || cut < 0 || cut > n || kmer < HM_SYMM_MIN_KMER)
+    return hm_set_error(HM_EINVAL,"hm_symm_align_cut: bad arguments");
+  const int psh = 64-2*(kmer>>1);
+  if (cut == 0 || cut == n)
+    { *out = cut; return HM_OK; }
+  uint64_t prev, buf[4096];
+  HM_CUDA(cudaMemcpy(&prev,d_keys+cut-1,sizeof(uint64_t),cudaMemcpyDeviceToHost));
+  while (cut < n)
+    { int64_t m = n-cut < 4096 ? n-cut : 4096;
+      HM_CUDA(cudaMemcpy(buf,d_keys+cut,sizeof(uint64_t)*(size_t) m,cudaMemcpyDeviceToHost));
+      for (int64_t i = 0; i < m; i++)
+        if (((buf[i] ^ prev) >> psh) != 0)
+          { *out = cut+i; return HM_OK; }
+      cut += m;
+    }
+  *out = n;
+  return HM_OK;
+}

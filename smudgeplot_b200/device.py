@@ -50,6 +50,10 @@ class DeviceTable:
         self.launches = 0
         self.shards = None          # _lib.Shards when the incidence array is sharded over GPUs
         self.deg_ptr = None         # raw device pointer overriding self.deg (IPC-shared allocation)
+        self.symmetric = None       # fingerprint verdict (None = not examined yet)
+        self.symm_layout = None     # _lib.SymmLayout + work area of the strand-symmetric scan
+        self.symm_work = None
+        self.symm_shards = None     # _lib.SymmShards when several GPUs share the scan
 
     # ---- construction -------------------------------------------------------------------
     @classmethod
@@ -83,16 +87,141 @@ class DeviceTable:
             return t
         return None
 
-    def build_index(self):
+    def build_index(self, direct: bool = True):
+        """bucket index (both paths) + the prefix filter of the direct search (`direct=False` skips
+        the filter: tables that pass the symmetry fingerprint never probe it)"""
         self.bucket = torch.empty((1 << self.bits) + 1, dtype=self.idx_dtype, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self.L.hm_k_build_bucket_index(_ptr(self.keys), self.n, self.bits,
                                                       _ptr(self.bucket), self.idx64, _stream()))
+        self.launches += 1
+        if direct:
+            self.build_filter()
+        return self
+
+    def build_filter(self):
         self.filter = torch.empty(self.L.hm_filter_words(self.fbits), dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self.L.hm_k_build_filter(_ptr(self.keys), self.n, self.fbits, _ptr(self.filter), _stream()))
-        self.launches += 2
+        self.launches += 1
         return self
+
+    # ---- strand-symmetric scan (csrc/hm_symm.cu) -----------------------------------------
+    def fingerprint(self, i0: int = 0, i1: int | None = None, seeds=None) -> torch.Tensor:
+        """keyed multiset fingerprints of {(x,cnt)} and {(rc x,cnt)} over entries [i0,i1): int64[4]
+        device tensor (sums mod 2^64; partial sums of several ranges / ranks just add up)"""
+        import ctypes as C
+        i1 = self.n if i1 is None else i1
+        sd = (C.c_uint64 * 2)()
+        if seeds is None:
+            self.L.hm_symm_seeds(sd)
+        else:
+            sd[0], sd[1] = seeds
+        acc = torch.zeros(4, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.hm_k_symm_fingerprint(_ptr(self.keys), _ptr(self.keys_lo), _ptr(self.cnt), i0, i1,
+                                                    self.kmer, sd, _ptr(acc), _stream()))
+        self.launches += 1
+        return acc
+
+    def check_symmetric(self) -> bool:
+        """does the table hold rc(x) with count(x) for every x?  (what examine_table's one-k-mer
+        probe stands for, PloidyPlot.c:1199-1229, verified for the whole table)"""
+        if self.kmer < 2:
+            self.symmetric = False
+        else:
+            a = self.fingerprint().tolist()
+            self.symmetric = (a[0] == a[2] and a[1] == a[3])
+        return self.symmetric
+
+    def align_cut(self, cut: int) -> int:
+        """next run boundary at or after `cut` (a run = entries sharing their first k/2 bases)"""
+        import ctypes as C
+        out = C.c_int64()
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.hm_symm_align_cut(_ptr(self.keys), self.n, self.kmer, int(cut), C.byref(out)))
+        return int(out.value)
+
+    def make_symm_shards(self, cuts, rank: int):
+        """_lib.SymmShards for run-aligned cuts [0, c1, ..., n] as seen from shard `rank`"""
+        sh = _lib.SymmShards()
+        sh.n_seg, sh.self_ = len(cuts) - 1, rank
+        for r, c in enumerate(cuts):
+            sh.off[r] = c
+        idx = torch.tensor([min(c, self.n - 1) for c in cuts[1:-1]], dtype=torch.int64, device=self.device)
+        first = self.keys[idx].tolist() if idx.numel() else []
+        for r, (c, v) in enumerate(zip(cuts[1:-1], first), start=1):
+            sh.first_key[r] = (v & 0xFFFFFFFFFFFFFFFF) if c < self.n else 0xFFFFFFFFFFFFFFFF
+        return sh
+
+    def alloc_symm(self, lo: int = 0, hi: int | None = None, shards=None):
+        """work area of the symmetric scan over [lo,hi); `shards` = _lib.SymmShards for several GPUs"""
+        import ctypes as C
+        hi = self.n if hi is None else hi
+        self.lo, self.hi = lo, hi
+        lay = _lib.SymmLayout()
+        nseg = shards.n_seg if shards is not None else 1
+        _lib.check(self.L.hm_symm_plan(self.n, hi - lo, self.kmer, nseg, C.byref(lay)))
+        self.symm_layout, self.symm_shards = lay, shards
+        self.symm_work = torch.empty(lay.bytes, dtype=torch.uint8, device=self.device)
+        if getattr(self, "plot", None) is None:
+            self.plot = torch.zeros(_lib.PLOT_CELLS, dtype=torch.int64, device=self.device)
+        return self
+
+    def bloom_view(self) -> torch.Tensor:
+        """int32[n_seg, seg_words] view of the Bloom segments inside the work area"""
+        lay = self.symm_layout
+        return self.symm_work[lay.off_bloom: lay.off_bloom + 4 * lay.seg_words * lay.n_seg].view(torch.int32) \
+                   .view(lay.n_seg, lay.seg_words)
+
+    def _symm_shards(self):
+        import ctypes as C
+        return C.byref(self.symm_shards) if self.symm_shards is not None else None
+
+    def runscan(self):
+        """'pass 1' of the symmetric scan over [lo,hi)"""
+        import ctypes as C
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.hm_k_symm_runscan(_ptr(self.keys), _ptr(self.keys_lo), _ptr(self.cnt), self.n,
+                                                _ptr(self.bucket), self.bits, self.idx64, self.kmer, self.lo, self.hi,
+                                                _ptr(self.symm_work), C.byref(self.symm_layout), self._symm_shards(),
+                                                _stream()))
+        self.launches += 1
+
+    def resolve(self):
+        """'pass 2' of the symmetric scan; accumulates into self.plot"""
+        import ctypes as C
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.hm_k_symm_resolve(_ptr(self.keys), _ptr(self.keys_lo), _ptr(self.cnt), self.n,
+                                                _ptr(self.bucket), self.bits, self.idx64, self.kmer,
+                                                _ptr(self.symm_work), C.byref(self.symm_layout), self._symm_shards(),
+                                                _ptr(self.plot), _stream()))
+        self.launches += 1
+
+    def symm_status(self):
+        """(candidate pairs, status bits) of the last symmetric scan; synchronises"""
+        import ctypes as C
+        nc, st = C.c_uint64(), C.c_uint64()
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.hm_symm_status(_ptr(self.symm_work), C.byref(self.symm_layout), C.byref(nc), C.byref(st),
+                                             _stream()))
+        return int(nc.value), int(st.value)
+
+    def scan_symm(self):
+        """both kernels of the symmetric scan on one GPU; -> plot int64[1001,501] (device tensor).
+        Raises if the status word says the table was not symmetric after all."""
+        if self.bucket is None:
+            self.build_index(direct=False)
+        if self.symm_work is None:
+            self.alloc_symm()
+        self.plot.zero_()
+        self.runscan()
+        self.resolve()
+        nc, st = self.symm_status()
+        if st != 0:
+            raise _lib.HetmersError(-1, f"symmetric scan: status {st} (1 = a reverse complement is missing, "
+                                        f"2 = candidate list overflow); use the direct passes")
+        return self.plot.view(_lib.SMAX + 1, _lib.PLOT_W)
 
     # ---- the two passes -----------------------------------------------------------------
     def alloc_work(self, lo: int = 0, hi: int | None = None):
@@ -126,10 +255,16 @@ class DeviceTable:
                                               self.lo, self.hi, _ptr(self.plot), self._shards(), _stream()))
         self.launches += 1
 
-    def scan(self):
-        """both passes on one GPU; -> plot int64[1001,501] (device tensor)"""
+    def scan(self, path: str = "auto"):
+        """one GPU; -> plot int64[1001,501] (device tensor).  path: "auto" = the symmetric scan when the
+        fingerprint says the table is strand-symmetric, else the direct passes; "direct" / "symm" force one"""
+        if path == "symm" or (path == "auto" and self.kmer >= 2 and
+                              (self.symmetric if self.symmetric is not None else self.check_symmetric())):
+            return self.scan_symm()
         if self.bucket is None:
             self.build_index()
+        if self.filter is None:
+            self.build_filter()
         if self.deg is None:
             self.alloc_work()
         else:

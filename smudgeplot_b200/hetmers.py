@@ -127,11 +127,18 @@ class Scan:
         self.nels = n.value
         return n.value
 
-    def run(self):
-        """-> (plot int64[1001,501], stats dict)"""
+    PATHS = {"auto": 0, "direct": 1, "symm": 2}
+
+    def is_symmetric(self) -> bool:
+        """whole-table verdict of the symmetry fingerprint (hm_scan_create / hm_scan_condition)"""
+        return bool(self._L.hm_scan_is_symmetric(self._h))
+
+    def run(self, path: str = "auto"):
+        """-> (plot int64[1001,501], stats dict).  path "auto": the strand-symmetric scan when the table
+        is symmetric, else the direct passes; "direct" / "symm" force one (stats["path"]: 1 / 2)"""
         plot = np.zeros(_lib.PLOT_CELLS, dtype=np.int64)
         st = _lib.ScanStats()
-        _lib.check(self._L.hm_scan_run(self._h, plot.ctypes.data, C.byref(st)))
+        _lib.check(self._L.hm_scan_run_path(self._h, self.PATHS[path], plot.ctypes.data, C.byref(st)))
         return plot.reshape(_lib.SMAX + 1, _lib.PLOT_W), st.as_dict()
 
     def extract(self, pixmap: np.ndarray):
