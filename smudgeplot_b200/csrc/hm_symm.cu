@@ -50,6 +50,7 @@
 #define RS_HALO    64                          /* entries staged on either side of the tile      */
 #define RS_WIN     (RS_TILE+2*RS_HALO)
 #define RS_SCANCAP RS_HALO                     /* longest run half scanned linearly               */
+#define RS_STAGE   768                         /* candidate records staged per CTA before they leave */
 
 #define SY_STATUS_ASYMMETRIC 1ull              /* a reverse complement was not in the table      */
 #define SY_STATUS_OVERFLOW   2ull              /* candidate list full                             */
@@ -66,16 +67,32 @@ struct SymmView
     unsigned long long cand_cap;
   };
 
-/* Bloom position of key (hi,lo): one bit in one 32-bit word of the owner's segment */
+/* Bloom slot of key (hi,lo): two bits of one 32-bit word of the owner's segment (one load per query) */
 template <int KW>
 __device__ __forceinline__ void bloom_slot(const SymmView &W, int seg, uint64_t hi, uint64_t lo,
-                                           uint32_t *&word, uint32_t &bit)
+                                           uint32_t *&word, uint32_t &mask)
 { uint64_t v = hi;
   if (KW == 2) v ^= lo * 0xD6E8FEB86659FD93ull;
   uint64_t m = v * 0x9E3779B97F4A7C15ull;
   uint32_t h = (uint32_t) (m >> 32);
   word = W.bloom + (size_t) seg * W.seg_words + __umulhi(h,W.seg_words);
-  bit  = 1u << ((uint32_t) (m >> 27) & 31);
+  mask = (1u << ((uint32_t) (m >> 27) & 31)) | (1u << ((uint32_t) (m >> 22) & 31));
+}
+
+/* L2 residency: the Bloom segments (tens of MB) are what pass 2 hits at random, the candidate records
+ * stream through once                                                                             */
+__device__ __forceinline__ uint32_t ld_keep(const uint32_t *p)
+{ uint32_t v; uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
+__device__ __forceinline__ uint64_t ld_stream(const uint64_t *p)
+{ uint64_t v, pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+  return v;
 }
 
 __device__ __forceinline__ int owner_of(const SymmView &W, uint64_t hi)
@@ -189,7 +206,8 @@ extern "C" void hm_symm_seeds(uint64_t seed[2])
 extern "C" int hm_symm_plan(int64_t n, int64_t range, int kmer, int n_seg, hm_symm_layout *out)
 { if (out == NULL || n < 0 || range < 0 || range > n || n_seg < 1 || n_seg > HM_MAX_SHARDS)
     return hm_set_error(HM_EINVAL,"hm_symm_plan: bad arguments");
-  int bits = 2;                                  /* Bloom bits per table entry (S is ~1/6 of the table) */
+  int bits = 1;                                  /* Bloom bits per table entry (S is ~1/6 of the table; two bits
+                                                  *   set per element): small enough to stay L2 resident          */
   const char *e = getenv("HETMERS_BLOOM_BITS");
   if (e != NULL && atoi(e) >= 1 && atoi(e) <= 64)
     bits = atoi(e);
@@ -239,6 +257,126 @@ static SymmView make_view(void *d_work, const hm_symm_layout *L, const hm_symm_s
 
 /* ------------------------------------------------------------------------ pass 1 -------- */
 
+/* shared-memory views of one CTA's window + its staging areas */
+template <int KW> struct RsSmem
+  { uint64_t *key, *klo;                /* window: RS_WIN slots                                   */
+    uint16_t *cnt;
+    uint64_t *ckey, *clo, *cmeta;       /* staged candidate records: RS_STAGE                     */
+    uint16_t *t1, *t2;                  /* task lists: heads of 2-entry runs / members of longer runs */
+  };
+
+/* stage one candidate record (warp-wide call; `emit` per lane) */
+template <int KW>
+__device__ __forceinline__ void stage_candidates(const RsSmem<KW> &S, unsigned *s_nc, const SymmView &W,
+                                                 bool emit, uint64_t x, uint64_t xl, uint64_t meta,
+                                                 int lane, unsigned lt)
+{ const unsigned bal = __ballot_sync(0xffffffffu,emit);
+  if (bal == 0)
+    return;
+  unsigned base = 0;
+  if (lane == 0)
+    base = atomicAdd(s_nc,(unsigned) __popc(bal));
+  base = __shfl_sync(0xffffffffu,base,0);
+  if (!emit)
+    return;
+  unsigned at = base + __popc(bal & lt);
+  if (at < RS_STAGE)
+    { S.ckey[at] = x;
+      if (KW == 2) S.clo[at] = xl;
+      S.cmeta[at] = meta;
+    }
+  else                                               /* staging full (dense tables): straight to the list */
+    { unsigned long long g1 = atomicAdd(W.cand_n,1ull);
+      if (g1 < W.cand_cap)
+        { W.cand_key[g1] = x;
+          if (KW == 2) W.cand_lo[g1] = xl;
+          W.cand_meta[g1] = meta;
+        }
+      else
+        atomicOr(W.status,SY_STATUS_OVERFLOW);
+    }
+}
+
+/* any member of a run of three or more: scan the run both ways (H, U, partner) and, for the lower
+ * member of a pair, the partner's H.  -> insert into the Bloom filter?  candidate record?          */
+template <typename IdxT, int KW>
+__device__ __forceinline__ void member_of_long_run(const RsSmem<KW> &S, int w, int v0, int v1, int64_t e0, int64_t e1,
+                                                   int64_t n, int64_t g, int kmer,
+                                                   const uint64_t *__restrict__ keys, const uint64_t *__restrict__ keys_lo,
+                                                   const uint16_t *__restrict__ cnt, const IdxT *__restrict__ bucket,
+                                                   int bshift, bool &insert, bool &emit, uint64_t &meta)
+{ const int Pr = kmer >> 1, pup = kmer-Pr, psh = 64-2*Pr;
+  const uint64_t x = S.key[w], xl = KW == 2 ? S.klo[w] : 0;
+  const int cx = S.cnt[w];
+  int  H = 0, U = 0, pj = -1, ppos = 0;
+  bool ovf = false;
+  int  b0, b1, j;
+  insert = false; emit = false; meta = 0;
+  { int lim = w-RS_SCANCAP > v0 ? w-RS_SCANCAP : v0;               /* backward half of the run */
+    for (j = w-1; j >= lim; j--)
+      { uint64_t z = S.key[j];
+        if (((z ^ x) >> psh) != 0) break;
+        int pos;
+        if (one_base_apart<KW>(x,xl,z,KW == 2 ? S.klo[j] : 0,pos) && cx + (int) S.cnt[j] <= HM_SMAX)
+          { H += 1; U += (pos >= pup); pj = j; ppos = pos; }
+      }
+    if (j < lim && !(lim == v0 && e0 == 0)) ovf = true;             /* run longer than the window */
+    b0 = j+1;
+  }
+  { int lim = w+RS_SCANCAP < v1-1 ? w+RS_SCANCAP : v1-1;           /* forward half */
+    for (j = w+1; j <= lim; j++)
+      { uint64_t z = S.key[j];
+        if (((z ^ x) >> psh) != 0) break;
+        int pos;
+        if (one_base_apart<KW>(x,xl,z,KW == 2 ? S.klo[j] : 0,pos) && cx + (int) S.cnt[j] <= HM_SMAX)
+          { H += 1; U += (pos >= pup); pj = j; ppos = pos; }
+      }
+    if (j > lim && !(lim == v1-1 && e1 == n)) ovf = true;
+    b1 = j;
+  }
+  if (!ovf)
+    { insert = (U > 0);
+      if (H == 1 && pj > w)                            /* x is the lower member: is y's only partner x? */
+        { uint64_t y = S.key[pj], yl = KW == 2 ? S.klo[pj] : 0;
+          const int cy = S.cnt[pj];
+          int Hy = 0;
+          for (j = b0; j < b1 && Hy < 2; j++)
+            { if (j == pj) continue;
+              int pos;
+              if (one_base_apart<KW>(y,yl,S.key[j],KW == 2 ? S.klo[j] : 0,pos) && cy + (int) S.cnt[j] <= HM_SMAX)
+                Hy += 1;
+            }
+          if (Hy == 1)
+            { emit = true;
+              meta = (uint64_t) cx | ((uint64_t) cy << 16) | ((uint64_t) ppos << 32) |
+                     ((uint64_t) base_at<KW>(y,yl,ppos) << 40);
+            }
+        }
+    }
+  else                                                 /* the run leaves the window: per-candidate look-ups */
+    { int64_t part;
+      neighbours_slow<IdxT,KW>(keys,keys_lo,cnt,bucket,bshift,kmer,Pr,pup,x,xl,cx,H,U,part,ppos);
+      insert = (U > 0);
+      if (H == 1 && part > g)
+        { uint64_t y = __ldg(keys+part), yl = KW == 2 ? __ldg(keys_lo+part) : 0;
+          const int cy = __ldg(cnt+part);
+          int Hy, Uy, py; int64_t party;
+          neighbours_slow<IdxT,KW>(keys,keys_lo,cnt,bucket,bshift,kmer,Pr,pup,y,yl,cy,Hy,Uy,party,py);
+          if (Hy == 1)
+            { emit = true;
+              meta = (uint64_t) cx | ((uint64_t) cy << 16) | ((uint64_t) ppos << 32) |
+                     ((uint64_t) base_at<KW>(y,yl,ppos) << 40);
+            }
+        }
+    }
+}
+
+/* Pass 1.  83 % of the entries of a genome-sized table are alone in their run (no other entry shares
+ * their first k/2 bases) and 15 % sit in a run of exactly two -- almost always the two alleles of one
+ * heterozygous site.  So every entry is first only CLASSIFIED against its two neighbours on either
+ * side (uniform, loop-free); heads of two-entry runs and members of longer runs are compacted into
+ * two task lists in shared memory and worked off with every lane busy.  (Scanning every entry's run
+ * in place cost 436 warp instructions per 32 entries at 34 % lane utilisation.)                     */
 template <typename IdxT, int KW>
 __global__ void __launch_bounds__(RS_THREADS)
 runscan_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ keys_lo,
@@ -246,9 +384,17 @@ runscan_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ k
                int kmer, int64_t lo, int64_t hi, int64_t tile0, int use_tma, const SymmView W)
 { extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t s_bar;
-  uint64_t *s_key = (uint64_t *) smem;
-  uint64_t *s_klo = s_key + (KW == 2 ? RS_WIN : 0);
-  uint16_t *s_cnt = (uint16_t *) (s_key + KW*RS_WIN);
+  __shared__ unsigned s_nc, s_n1, s_n2;
+  __shared__ unsigned long long s_base;
+  RsSmem<KW> S;
+  S.key   = (uint64_t *) smem;
+  S.klo   = S.key + (KW == 2 ? RS_WIN : 0);
+  S.ckey  = S.key + KW*RS_WIN;
+  S.clo   = S.ckey + (KW == 2 ? RS_STAGE : 0);
+  S.cmeta = S.ckey + KW*RS_STAGE;
+  S.cnt   = (uint16_t *) (S.cmeta + RS_STAGE);
+  S.t1    = S.cnt + RS_WIN;
+  S.t2    = S.t1 + RS_TILE/2;
 
   const int      Pr   = kmer >> 1;                 /* run = entries sharing their first Pr bases     */
   const int      pup  = kmer - Pr;                 /* positions >= pup have a mirror position < Pr   */
@@ -266,125 +412,133 @@ runscan_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ k
   /* ---- stage the window: TMA bulk copies for the 16-byte multiple, plain loads for the rest ---- */
   const int m   = v1-v0;
   const int mt  = use_tma ? (m & ~7) : 0;
-  if (threadIdx.x == 0 && mt > 0)
-    { mbar_init(&s_bar,1);
-      fence_proxy_async_smem();
+  if (threadIdx.x == 0)
+    { s_nc = 0; s_n1 = 0; s_n2 = 0;
+      if (mt > 0)
+        { mbar_init(&s_bar,1);
+          fence_proxy_async_smem();
+        }
     }
   __syncthreads();
   if (threadIdx.x == 0 && mt > 0)
     { mbar_arrive_expect_tx(&s_bar,(unsigned) (mt*(8*KW+2)));
-      bulk_copy_g2s(s_key+v0,keys+e0,(unsigned) (8*mt),&s_bar);
+      bulk_copy_g2s(S.key+v0,keys+e0,(unsigned) (8*mt),&s_bar);
       if (KW == 2)
-        bulk_copy_g2s(s_klo+v0,keys_lo+e0,(unsigned) (8*mt),&s_bar);
-      bulk_copy_g2s(s_cnt+v0,cnt+e0,(unsigned) (2*mt),&s_bar);
+        bulk_copy_g2s(S.klo+v0,keys_lo+e0,(unsigned) (8*mt),&s_bar);
+      bulk_copy_g2s(S.cnt+v0,cnt+e0,(unsigned) (2*mt),&s_bar);
     }
   for (int j = mt + threadIdx.x; j < m; j += RS_THREADS)
-    { s_key[v0+j] = keys[e0+j];
-      if (KW == 2) s_klo[v0+j] = keys_lo[e0+j];
-      s_cnt[v0+j] = cnt[e0+j];
+    { S.key[v0+j] = keys[e0+j];
+      if (KW == 2) S.klo[v0+j] = keys_lo[e0+j];
+      S.cnt[v0+j] = cnt[e0+j];
     }
   __syncthreads();
   if (mt > 0)
     mbar_wait(&s_bar,0);
 
-#pragma unroll 1
+  /* ---- classify: singleton / head of a two-entry run / member of a longer run ---- */
+#pragma unroll
   for (int e = 0; e < RS_EPT; e++)
     { const int     t = threadIdx.x + e*RS_THREADS;
       const int     w = t + RS_HALO;
       const int64_t g = T0+t;
-      const bool    active = (g >= lo && g < hi);
+      bool two = false, more = false;
+      if (g >= lo && g < hi)
+        { const uint64_t x = S.key[w];
+          const bool sp  = (w-1 >= v0) && (((S.key[w-1] ^ x) >> psh) == 0);
+          const bool sn  = (w+1 <  v1) && (((S.key[w+1] ^ x) >> psh) == 0);
+          if (sp | sn)
+            { const bool sp2 = (w-2 >= v0) && (((S.key[w-2] ^ x) >> psh) == 0);
+              const bool sn2 = (w+2 <  v1) && (((S.key[w+2] ^ x) >> psh) == 0);
+              more = (sp && sn) || (sn && sn2) || (sp && sp2);
+              two  = !more && sn;                       /* head of a run of exactly two (the tail stays silent) */
+            }
+        }
+      unsigned bal = __ballot_sync(FULL,two);
+      if (bal != 0)
+        { unsigned base = 0;
+          if (lane == 0) base = atomicAdd(&s_n1,(unsigned) __popc(bal));
+          base = __shfl_sync(FULL,base,0);
+          if (two) S.t1[base + __popc(bal & lt)] = (uint16_t) w;
+        }
+      bal = __ballot_sync(FULL,more);
+      if (bal != 0)
+        { unsigned base = 0;
+          if (lane == 0) base = atomicAdd(&s_n2,(unsigned) __popc(bal));
+          base = __shfl_sync(FULL,base,0);
+          if (more) S.t2[base + __popc(bal & lt)] = (uint16_t) w;
+        }
+    }
+  __syncthreads();
+
+  /* ---- runs of two: one comparison settles both members ---- */
+  const int n1 = (int) s_n1, n2 = (int) s_n2;
+  for (int i0 = (threadIdx.x & ~31); i0 < n1; i0 += RS_THREADS)
+    { const int i = i0+lane;
+      bool     emit = false;
+      uint64_t x = 0, xl = 0, meta = 0;
+      if (i < n1)
+        { const int w = S.t1[i];
+          x = S.key[w];
+          const uint64_t y = S.key[w+1];
+          uint64_t yl = 0;
+          if (KW == 2) { xl = S.klo[w]; yl = S.klo[w+1]; }
+          const int cx = S.cnt[w], cy = S.cnt[w+1];
+          int pos;
+          if (one_base_apart<KW>(x,xl,y,yl,pos) && cx+cy <= HM_SMAX)      /* H(x) = H(y) = 1 */
+            { emit = true;
+              meta = (uint64_t) cx | ((uint64_t) cy << 16) | ((uint64_t) pos << 32) |
+                     ((uint64_t) base_at<KW>(y,yl,pos) << 40);
+              if (pos >= pup)                                              /* U(x) = U(y) = 1: both are in S */
+                { uint32_t *word, mask;
+                  bloom_slot<KW>(W,W.self,x,xl,word,mask);
+                  atomicOr(word,mask);
+                  bloom_slot<KW>(W,W.self,y,yl,word,mask);
+                  atomicOr(word,mask);
+                }
+            }
+        }
+      stage_candidates<KW>(S,&s_nc,W,emit,x,xl,meta,lane,lt);
+    }
+
+  /* ---- longer runs: every member on its own ---- */
+  for (int i0 = (threadIdx.x & ~31); i0 < n2; i0 += RS_THREADS)
+    { const int i = i0+lane;
       bool     emit = false, insert = false;
       uint64_t x = 0, xl = 0, meta = 0;
-      if (active)
-        { x = s_key[w];
-          if (KW == 2) xl = s_klo[w];
-          const int cx = s_cnt[w];
-          int  H = 0, U = 0, pj = -1, ppos = 0;
-          bool ovf = false;
-          int  b0, b1, j;
-          /* backward half of the run */
-          { int lim = w-RS_SCANCAP > v0 ? w-RS_SCANCAP : v0;
-            for (j = w-1; j >= lim; j--)
-              { uint64_t z = s_key[j];
-                if (((z ^ x) >> psh) != 0) break;
-                int pos;
-                if (one_base_apart<KW>(x,xl,z,KW == 2 ? s_klo[j] : 0,pos) && cx + (int) s_cnt[j] <= HM_SMAX)
-                  { H += 1; U += (pos >= pup); pj = j; ppos = pos; }
-              }
-            if (j < lim && !(lim == v0 && e0 == 0)) ovf = true;     /* run longer than the window */
-            b0 = j+1;
-          }
-          /* forward half */
-          { int lim = w+RS_SCANCAP < v1-1 ? w+RS_SCANCAP : v1-1;
-            for (j = w+1; j <= lim; j++)
-              { uint64_t z = s_key[j];
-                if (((z ^ x) >> psh) != 0) break;
-                int pos;
-                if (one_base_apart<KW>(x,xl,z,KW == 2 ? s_klo[j] : 0,pos) && cx + (int) s_cnt[j] <= HM_SMAX)
-                  { H += 1; U += (pos >= pup); pj = j; ppos = pos; }
-              }
-            if (j > lim && !(lim == v1-1 && e1 == n)) ovf = true;
-            b1 = j;
-          }
-          if (!ovf)
-            { insert = (U > 0);
-              if (H == 1 && pj > w)                      /* x is the lower member: is y's only partner x? */
-                { uint64_t y = s_key[pj], yl = KW == 2 ? s_klo[pj] : 0;
-                  const int cy = s_cnt[pj];
-                  int Hy = 0;
-                  for (j = b0; j < b1 && Hy < 2; j++)
-                    { if (j == pj) continue;
-                      int pos;
-                      if (one_base_apart<KW>(y,yl,s_key[j],KW == 2 ? s_klo[j] : 0,pos) &&
-                          cy + (int) s_cnt[j] <= HM_SMAX)
-                        Hy += 1;
-                    }
-                  if (Hy == 1)
-                    { emit = true;
-                      meta = (uint64_t) cx | ((uint64_t) cy << 16) | ((uint64_t) ppos << 32) |
-                             ((uint64_t) base_at<KW>(y,yl,ppos) << 40);
-                    }
-                }
-            }
-          else
-            { int64_t part;
-              neighbours_slow<IdxT,KW>(keys,keys_lo,cnt,bucket,bshift,kmer,Pr,pup,x,xl,cx,H,U,part,ppos);
-              insert = (U > 0);
-              if (H == 1 && part > g)
-                { uint64_t y = __ldg(keys+part), yl = KW == 2 ? __ldg(keys_lo+part) : 0;
-                  const int cy = __ldg(cnt+part);
-                  int Hy, Uy, py; int64_t party;
-                  neighbours_slow<IdxT,KW>(keys,keys_lo,cnt,bucket,bshift,kmer,Pr,pup,y,yl,cy,Hy,Uy,party,py);
-                  if (Hy == 1)
-                    { emit = true;
-                      meta = (uint64_t) cx | ((uint64_t) cy << 16) | ((uint64_t) ppos << 32) |
-                             ((uint64_t) base_at<KW>(y,yl,ppos) << 40);
-                    }
-                }
-            }
+      if (i < n2)
+        { const int w = S.t2[i];
+          x = S.key[w];
+          if (KW == 2) xl = S.klo[w];
+          member_of_long_run<IdxT,KW>(S,w,v0,v1,e0,e1,n,T0+(w-RS_HALO),kmer,keys,keys_lo,cnt,bucket,bshift,
+                                      insert,emit,meta);
         }
       if (insert)
-        { uint32_t *word, bit;
-          bloom_slot<KW>(W,W.self,x,xl,word,bit);
-          atomicOr(word,bit);
+        { uint32_t *word, mask;
+          bloom_slot<KW>(W,W.self,x,xl,word,mask);
+          atomicOr(word,mask);
         }
-      const unsigned bal = __ballot_sync(FULL,emit);
-      if (bal != 0)
-        { unsigned long long base = 0;
-          if (lane == 0)
-            base = atomicAdd(W.cand_n,(unsigned long long) __popc(bal));
-          base = __shfl_sync(FULL,base,0);
-          if (emit)
-            { unsigned long long at = base + __popc(bal & lt);
-              if (at < W.cand_cap)
-                { W.cand_key[at] = x;
-                  if (KW == 2) W.cand_lo[at] = xl;
-                  W.cand_meta[at] = meta;
-                }
-              else
-                atomicOr(W.status,SY_STATUS_OVERFLOW);
-            }
+      stage_candidates<KW>(S,&s_nc,W,emit,x,xl,meta,lane,lt);
+    }
+
+  /* ---- the staged records leave the CTA in one piece: one global atomic per CTA (one per record, or
+   *      per warp, on the one list counter serialises in L2: 9.2 ms for 1.8e7 records)            ---- */
+  __syncthreads();
+  const unsigned nc = s_nc < RS_STAGE ? s_nc : RS_STAGE;
+  if (nc == 0)
+    return;
+  if (threadIdx.x == 0)
+    s_base = atomicAdd(W.cand_n,(unsigned long long) nc);
+  __syncthreads();
+  for (unsigned i = threadIdx.x; i < nc; i += RS_THREADS)
+    { unsigned long long at = s_base + i;
+      if (at < W.cand_cap)
+        { W.cand_key[at] = S.ckey[i];
+          if (KW == 2) W.cand_lo[at] = S.clo[i];
+          W.cand_meta[at] = S.cmeta[i];
         }
+      else
+        atomicOr(W.status,SY_STATUS_OVERFLOW);
     }
 }
 
@@ -392,7 +546,15 @@ template <typename IdxT, int KW>
 static cudaError_t launch_runscan(const uint64_t *keys, const uint64_t *keys_lo, const uint16_t *cnt, int64_t n,
                                   const void *bucket, int bits, int kmer, int64_t lo, int64_t hi,
                                   const SymmView &W, cudaStream_t st)
-{ size_t smem = (size_t) RS_WIN*(8*KW+2);                    /* 21.8 / 39.2 KB: below the 48 KB default */
+{ static int configured[64] = {0};                            /* per instantiation */
+  size_t smem = (size_t) RS_WIN*(8*KW+2) + (size_t) RS_STAGE*8*(KW+1) + 2*(RS_TILE/2+RS_TILE);   /* 40 KB (k <= 32) / 64 KB */
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (smem > 48*1024 && (dev >= 64 || !configured[dev]))
+    { cudaError_t e = cudaFuncSetAttribute(runscan_kernel<IdxT,KW>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem);
+      if (e != cudaSuccess) return e;
+      if (dev < 64) configured[dev] = 1;
+    }
   int64_t tile0 = lo/RS_TILE, tile1 = (hi+RS_TILE-1)/RS_TILE;
   int     tma   = ((((uintptr_t) keys) | ((uintptr_t) cnt) | ((uintptr_t) (keys_lo ? keys_lo : keys))) & 15) == 0;
   runscan_kernel<IdxT,KW><<<(unsigned) (tile1-tile0),RS_THREADS,smem,st>>>
@@ -436,8 +598,8 @@ extern "C" int hm_k_symm_runscan(const uint64_t *d_keys, const uint64_t *d_keys_
 
 /* ------------------------------------------------------------------------ pass 2 -------- */
 
-#define RV_TS 192      /* shared-memory plot tile: sums < 192, mins < 96 (72 KB) */
-#define RV_TM 96
+#define RV_TS 192      /* shared-memory plot tile: sums < 192, mins < 88 (66 KB; 3 CTAs per SM with the queues) */
+#define RV_TM 88
 #define RV_THREADS 512
 #define RV_CTAS_PER_SM 3
 
@@ -474,44 +636,102 @@ __device__ __noinline__ bool has_upper_partner(const uint64_t *__restrict__ keys
   return (U > 0);
 }
 
+/* one candidate: are rc x / rc y in S?  Bloom bits first; `exact` = also settle the hits.
+ * -> 0 isolated pair, 1 not isolated, 2 undecided (a Bloom hit, exact == false)                  */
+template <typename IdxT, int KW, bool EXACT>
+__device__ __forceinline__ int judge_candidate(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ keys_lo,
+                                               const uint16_t *__restrict__ cnt, int64_t n,
+                                               const IdxT *__restrict__ bucket, int bshift, int kmer,
+                                               const SymmView &W, uint64_t x, uint64_t xl, uint64_t meta)
+{ const int p  = (int) ((meta >> 32) & 0xff), yb = (int) ((meta >> 40) & 3);
+  uint64_t rx, rxl, ry, ryl;
+  revcomp_kmer<KW>(x,xl,kmer,rx,rxl);
+  ry = rx; ryl = rxl;
+  set_base<KW>(ry,ryl,kmer-1-p,3-yb);                      /* rc y = rc x with the mirrored base swapped */
+  uint32_t *wa, *wb, ba, bb;
+  bloom_slot<KW>(W,W.n_seg > 1 ? owner_of(W,rx) : 0,rx,rxl,wa,ba);
+  bloom_slot<KW>(W,W.n_seg > 1 ? owner_of(W,ry) : 0,ry,ryl,wb,bb);
+  const bool ha = (ld_keep(wa) & ba) == ba, hb = (ld_keep(wb) & bb) == bb;
+  if (!ha && !hb)
+    return 0;
+  if (!EXACT)
+    return 2;
+  if (ha && has_upper_partner<IdxT,KW>(keys,keys_lo,cnt,n,bucket,bshift,kmer,rx,rxl,W.status))
+    return 1;
+  if (hb && has_upper_partner<IdxT,KW>(keys,keys_lo,cnt,n,bucket,bshift,kmer,ry,ryl,W.status))
+    return 1;
+  return 0;
+}
+
+__device__ __forceinline__ void count_pair(uint32_t *tile, unsigned long long *__restrict__ plot,
+                                           uint64_t meta, int kmer)
+{ const int cx = (int) (meta & 0xffff), cy = (int) ((meta >> 16) & 0xffff);
+  const int p  = (int) ((meta >> 32) & 0xff);
+  const unsigned wgt = (2*p == kmer-1) ? 1u : 2u;          /* middle base: the mirror pair is found itself */
+  const int s = cx+cy;
+  const int m = cx < cy ? cx : cy;
+  if (s < RV_TS && m < RV_TM)
+    atomicAdd(tile + s*RV_TM + m, wgt);
+  else
+    atomicAdd(plot + s*HM_PLOT_W + m, (unsigned long long) wgt);
+}
+
+/* Candidates whose Bloom look-ups both miss (~85 %) are counted at once.  The others need the exact
+ * answer -- a bucket look-up and a run scan per hit, ~5 dependent random accesses -- and a warp in
+ * which one lane does that stalls all 32: they are parked in a per-warp queue and settled 32 at a
+ * time, every lane busy.                                                                           */
 template <typename IdxT, int KW>
 __global__ void __launch_bounds__(RV_THREADS,RV_CTAS_PER_SM)
 resolve_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ keys_lo,
                const uint16_t *__restrict__ cnt, int64_t n, const IdxT *__restrict__ bucket, int bshift,
                int kmer, const SymmView W, unsigned long long *__restrict__ plot)
 { extern __shared__ uint32_t tile[];
+  __shared__ uint32_t s_q[RV_THREADS/32][64];
+  const unsigned FULL = 0xffffffffu;
+  const int      lane = threadIdx.x & 31;
+  const unsigned lt   = (1u << lane) - 1;
+  uint32_t *q  = s_q[threadIdx.x >> 5];
+  int       qn = 0;
   for (int t = threadIdx.x; t < RV_TS*RV_TM; t += blockDim.x)
     tile[t] = 0;
   __syncthreads();
-  unsigned long long nc = *W.cand_n;
-  if (nc > W.cand_cap) nc = W.cand_cap;
+  unsigned long long ncl = *W.cand_n;
+  if (ncl > W.cand_cap) ncl = W.cand_cap;
+  const int64_t nc     = (int64_t) ncl;
   const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t) nc; i += stride)
-    { const uint64_t x = W.cand_key[i], xl = KW == 2 ? W.cand_lo[i] : 0, meta = W.cand_meta[i];
-      const int cx = (int) (meta & 0xffff), cy = (int) ((meta >> 16) & 0xffff);
-      const int p  = (int) ((meta >> 32) & 0xff), yb = (int) ((meta >> 40) & 3);
-      uint64_t rx, rxl, ry, ryl;
-      revcomp_kmer<KW>(x,xl,kmer,rx,rxl);
-      ry = rx; ryl = rxl;
-      set_base<KW>(ry,ryl,kmer-1-p,3-yb);                    /* rc y = rc x with the mirrored base swapped */
-      uint32_t *wa, *wb, ba, bb;
-      bloom_slot<KW>(W,W.n_seg > 1 ? owner_of(W,rx) : 0,rx,rxl,wa,ba);
-      bloom_slot<KW>(W,W.n_seg > 1 ? owner_of(W,ry) : 0,ry,ryl,wb,bb);
-      const uint32_t va = __ldg(wa), vb = __ldg(wb);
-      bool taint = false;
-      if ((va & ba) != 0)
-        taint = has_upper_partner<IdxT,KW>(keys,keys_lo,cnt,n,bucket,bshift,kmer,rx,rxl,W.status);
-      if (!taint && (vb & bb) != 0)
-        taint = has_upper_partner<IdxT,KW>(keys,keys_lo,cnt,n,bucket,bshift,kmer,ry,ryl,W.status);
-      if (taint)
-        continue;
-      const unsigned wgt = (2*p == kmer-1) ? 1u : 2u;          /* middle base: the mirror pair is found itself */
-      const int s = cx+cy;
-      const int m = cx < cy ? cx : cy;
-      if (s < RV_TS && m < RV_TM)
-        atomicAdd(tile + s*RV_TM + m, wgt);
-      else
-        atomicAdd(plot + s*HM_PLOT_W + m, (unsigned long long) wgt);
+  const int64_t first  = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint32_t it = 0; first-lane + (int64_t) it*stride < nc; it++)
+    { const int64_t i = first + (int64_t) it*stride;
+      bool pend = false;
+      if (i < nc)
+        { const uint64_t x = ld_stream(W.cand_key+i), xl = KW == 2 ? ld_stream(W.cand_lo+i) : 0,
+                         meta = ld_stream(W.cand_meta+i);
+          int v = judge_candidate<IdxT,KW,false>(keys,keys_lo,cnt,n,bucket,bshift,kmer,W,x,xl,meta);
+          if (v == 0)
+            count_pair(tile,plot,meta,kmer);
+          pend = (v == 2);
+        }
+      const unsigned bal = __ballot_sync(FULL,pend);
+      if (pend)
+        q[qn + __popc(bal & lt)] = (it << 5) | (uint32_t) lane;
+      qn += __popc(bal);
+      __syncwarp();
+      if (qn >= 32)
+        { qn -= 32;
+          const uint32_t e = q[qn+lane];
+          __syncwarp();
+          const int64_t j = first-lane + (int64_t) (e & 31) + (int64_t) (e >> 5)*stride;
+          const uint64_t x = W.cand_key[j], xl = KW == 2 ? W.cand_lo[j] : 0, meta = W.cand_meta[j];
+          if (judge_candidate<IdxT,KW,true>(keys,keys_lo,cnt,n,bucket,bshift,kmer,W,x,xl,meta) == 0)
+            count_pair(tile,plot,meta,kmer);
+        }
+    }
+  if (lane < qn)
+    { const uint32_t e = q[lane];
+      const int64_t j = first-lane + (int64_t) (e & 31) + (int64_t) (e >> 5)*stride;
+      const uint64_t x = W.cand_key[j], xl = KW == 2 ? W.cand_lo[j] : 0, meta = W.cand_meta[j];
+      if (judge_candidate<IdxT,KW,true>(keys,keys_lo,cnt,n,bucket,bshift,kmer,W,x,xl,meta) == 0)
+        count_pair(tile,plot,meta,kmer);
     }
   __syncthreads();
   for (int t = threadIdx.x; t < RV_TS*RV_TM; t += blockDim.x)
