@@ -9,13 +9,20 @@ A "step" is one full scan (pass 1 + degree exchange + pass 2 + plot reduce = T_s
 table, het 1 %, coverage 40x, L=12, ~2e8 k-mers per GPU (weak scaling: with N GPUs the table has
 N x 2e8 k-mers, every rank holds a replica and scans a contiguous 1/N index range).
 
-  value  k-mers/s with the table already unpacked in HBM (CUDA events, max over ranks)
+  value  k-mers/s with the table already unpacked in HBM (CUDA events, max over ranks).  The table is
+         strand-symmetric (as the reference requires of its input), so the scan is the symmetric one
+         of csrc/hm_symm.cu: runscan_kernel + resolve_kernel (HETMERS_PATH=direct: the direct passes)
   e2e    k-mers/s through the public C-ABI call hm_hetmers_host() on HOST buffers holding the raw
-         FastK part payloads in pinned memory: H2D + unpack + bucket index + both passes + plot D2H
-  roofline   pass-1 kernel (dominant): algorithmic bytes A = 2*TBYTE+2 = 22 B/k-mer
-             x k-mers per launch / average launch time, against MEASURED_PEAKS.json hbm_gbs
+         FastK part payloads in pinned memory: H2D + unpack + bucket index + symmetry fingerprint +
+         both kernels + plot D2H
+  roofline   dominant kernel (runscan_kernel): it reads every entry once, TBYTE = 10 B/k-mer at k=31
+             (the official whole-scan figure of SURVEY §8d, A = 2*TBYTE+2 = 22 B/k-mer over T_scan, is
+             reported next to it as roofline.whole_scan), against MEASURED_PEAKS.json hbm_gbs
+  parity     hard gates (non-zero exit): the timed table's plot == the plot of the independent direct
+             passes; N > 1: the sharded plot == a one-GPU scan of the same table on rank 0; the .smu
+             of our executable == the reference binary's on the same files
   cpu_baseline  the reference C hetmers (oracle/_ref/hetmers; else the oracle port) on the host
-             cores, on a bounded sample of the same workload
+             cores, on the SAME table files our executable reads (e2e_exec)
 Inputs (1.9 GB table + 0.27 GB bucket index per 2e8 k-mers) exceed the 126 MB L2, so no flush is
 needed between timed iterations.
 """
@@ -32,7 +39,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 K, PLOIDY, HET, COV, LCUT, SEED = 31, 2, 0.01, 40.0, 12, 2
-ALGO_BYTES_PER_KMER = 2 * ((K + 3) // 4 + 2) + 2          # 22 B at k=31
+TBYTE = (K + 3) // 4 + 2                                   # packed k-mer + uint16 count: 10 B at k=31
+ALGO_BYTES_PER_KMER = 2 * TBYTE + 2                        # 22 B at k=31: two passes + deg byte
 UNIT = "k-mers/s"
 
 
@@ -167,10 +175,20 @@ def time_reference(table, nels, threads, runs=1):
 
 
 def cpu_sample_size(args, threads):
-    # survey anchor ~0.45e6 k-mers/s per thread at k=31, but the reference stops scaling
-    # near 8-9e6 k-mers/s (measured: 8.4e6/s at -T64 on the 128-core B200 host); bounded by the GPU workload
+    # reference arm: survey anchor ~0.45e6 k-mers/s per thread at k=31, but the reference stops
+    # scaling near 8-9e6 k-mers/s (measured: 7.8e6/s at -T64 on a B200 host); bounded by the GPU workload
     n = min(0.45e6 * threads, 9e6) * args.cpu_seconds
     return int(max(2e6, min(n, args.nels)))
+
+
+def bench_config(world, nels=None, extra=None):
+    """the `config` object both arms print (same keys, same workload)"""
+    c = {"workload": workload_name(world), "k": K, "ploidy": PLOIDY, "het": HET, "cov": COV, "L": LCUT, "seed": SEED}
+    if nels is not None:
+        c["nels"] = nels
+    if extra:
+        c.update(extra)
+    return c
 
 
 def run_reference_arm(args):
@@ -194,10 +212,12 @@ def run_reference_arm(args):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
                 "data": "synthetic", "gpu_launches": 0,
-                "config": {"workload": workload_name(args.gpus), "k": K, "nels_sample": nels},
+                "config": bench_config(args.gpus),
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
-                                 "sample": f"one pass of the {'reference C hetmers' if kind == 'reference' else 'oracle port'} "
-                                           f"-T{threads} over a seeded {nels}-k-mer table of the same workload per step"},
+                                 "sample": f"per step one pass of the {'reference C hetmers' if kind == 'reference' else 'oracle port'} "
+                                           f"-T{threads} over a seeded {nels}-k-mer table of this workload (same generator, "
+                                           f"parameters and seed as the GPU arm's table; the reference is linear in the "
+                                           f"table size, BASELINE.md §2)", "nels_sample": nels},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
     finally:
@@ -217,16 +237,19 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def measured_traffic(nels):
-    """dram bytes per pass-1 launch from the committed ncu --set full capture, scaled per k-mer"""
-    p = os.path.join(ROOT, "profiles", "pass1_traffic.json")
-    if os.path.exists(p):
-        try:
-            j = json.load(open(p))
-            return float(j["dram_bytes_per_kmer"]) * nels
-        except Exception:
-            pass
-    return None
+def measured_traffic(kernel, nels, grid):
+    """dram bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json),
+    scaled per k-mer.  The record names the launch shape it was captured with: a record of another shape
+    (entries per CTA) is refused rather than quoted."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        j = json.load(open(p))[kernel]
+        if grid is not None and j.get("entries_per_cta") is not None and \
+                abs(nels / grid - j["entries_per_cta"]) > 0.02 * j["entries_per_cta"]:
+            return None
+        return float(j["dram_bytes_per_kmer"]) * nels
+    except Exception:
+        return None
 
 
 def run_ours(args):
@@ -256,21 +279,37 @@ def run_ours(args):
     # ---- synthetic table (setup, untimed) ---------------------------------------------------
     n_target = int(args.nels) * world
     G = synth.calibrate_G(K, n_target, PLOIDY, HET, COV, LCUT)
+    want_direct = os.environ.get("HETMERS_PATH") == "direct"
     if multi:
         job = hdist.ShardedScan.from_synthetic(K, G, PLOIDY, HET, COV, LCUT, SEED, dev)
         nels, my_n = job.n_total, job.hi - job.lo
+        path = job.path
+        table = job.table
     else:
         keys, cnt = synth.synth_table(K, G, PLOIDY, HET, COV, LCUT, SEED, device=dev)
-        table = DeviceTable(K, keys, cnt.to(torch.int16)).build_index()
-        table.alloc_work()
+        table = DeviceTable(K, keys, cnt.to(torch.int16)).build_index(direct=False)
+        path = "symm" if (table.check_symmetric() and not want_direct) else "direct"
+        if path == "symm":
+            table.alloc_symm()
+        else:
+            table.build_filter()
+            table.alloc_work()
         nels = my_n = table.n
     torch.cuda.synchronize()
 
     def one_scan(events=None):
         if multi:
             return job.scan(events)
-        table.deg.zero_()
         table.plot.zero_()
+        if path == "symm":
+            if events is not None:
+                events[0].record()
+            table.runscan()
+            if events is not None:
+                events[1].record()
+            table.resolve()
+            return table.plot
+        table.deg.zero_()
         if events is not None:
             events[0].record()
         table.pass1()
@@ -300,6 +339,7 @@ def run_ours(args):
             dist.barrier()
         ms_total = ev0.elapsed_time(ev1)
         ms_p1 = sum(a.elapsed_time(b) for a, b in p1) / args.steps
+        timed_plot = plot.clone()
         # keep the sampler alive over the e2e region too (more samples under load)
         e2e = None
         if multi:
@@ -313,62 +353,152 @@ def run_ours(args):
         ms_total, ms_p1 = t.tolist()
     ms_step = ms_total / args.steps
     value = nels / (ms_step * 1e-3)
-    launches = (3 if multi else 2) * args.steps
+    # kernels of ours per scan: runscan + resolve (symmetric) / pass 1 + pass 2 (+ deferred look-ups, N > 1)
+    launches = (2 if (path == "symm" or not multi) else 3) * args.steps
+
+    # ---- parity gates (untimed): the timed plot against independent computations of the same table ----
+    parity = {"path": path}
+    ok = True
+    if path == "symm":
+        clean = job.symm_ok() if multi else (table.symm_status()[1] == 0)
+        parity["symmetric_scan_status_clean"] = bool(clean)
+        ok &= bool(clean)
+    if rank == 0:
+        ref_t = DeviceTable(K, table.keys, table.cnt, bits=table.bits)
+        ref_t.bucket = table.bucket
+        ref_t.build_filter()
+        ref_t.alloc_work()
+        direct_plot = ref_t.scan("direct").reshape(-1).clone()          # the direct passes: another algorithm
+        parity["vs_direct_passes_one_gpu"] = bool(torch.equal(direct_plot, timed_plot.reshape(-1)))
+        ok &= parity["vs_direct_passes_one_gpu"]
+        if multi:
+            one = DeviceTable(K, table.keys, table.cnt, bits=table.bits)
+            one.bucket = table.bucket
+            one_plot = one.scan("symm" if path == "symm" else "direct").reshape(-1).clone()
+            parity["vs_single_gpu"] = bool(torch.equal(one_plot, timed_plot.reshape(-1)))
+            ok &= parity["vs_single_gpu"]
+            del one
+        parity["pairs_counted"] = int(timed_plot.sum())
+        del ref_t, direct_plot
+        torch.cuda.empty_cache()
 
     peak, peak_src = peaks()
-    per_launch = nels / world
-    achieved = ALGO_BYTES_PER_KMER * per_launch / (ms_p1 * 1e-3) / 1e9
+    per_launch = my_n
+    kname = "runscan_kernel" if path == "symm" else "pass1_filter_kernel"
+    kbytes = TBYTE if path == "symm" else ALGO_BYTES_PER_KMER
+    achieved = kbytes * per_launch / (ms_p1 * 1e-3) / 1e9
+    whole = ALGO_BYTES_PER_KMER * nels / world / (ms_step * 1e-3) / 1e9
+    grid = (per_launch + 2047) // 2048 if path == "symm" else None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(world), "k": K, "ploidy": PLOIDY, "het": HET, "cov": COV, "L": LCUT,
-                       "nels": nels, "nels_per_gpu": my_n, "seed": SEED, "bucket_bits": (job.bits if multi else table.bits),
-                       "filter_bits": (job.table.fbits if multi else table.fbits),
-                       "parallelism": f"table replica per GPU, {world} contiguous index shards; degree exchange: {job.exchange}" if multi else "1 GPU",
-                       "l2": "inputs (>=1.9 GB table + bucket index per GPU) exceed the 126 MB L2; no flush between iterations"},
-            "clocks": clk.summary(), "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "pass1_filter_kernel", "achieved": achieved, "peak": peak,
+            "config": bench_config(world, nels, {
+                "nels_per_gpu": my_n, "bucket_bits": table.bits, "scan": path,
+                "parallelism": (f"table replica per GPU, {world} contiguous run-aligned index shards; exchange: {job.exchange}"
+                                if multi else "1 GPU"),
+                "l2": "inputs (>=1.9 GB table + bucket index per GPU) exceed the 126 MB L2; no flush between iterations"}),
+            "clocks": clk.summary(), "gpu_launches": launches, "parity": parity,
+            "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                         "algorithmic_bytes_per_kmer": ALGO_BYTES_PER_KMER, "ms_per_launch": ms_p1,
-                         "traffic": measured_traffic(per_launch)}}
+                         "algorithmic_bytes_per_kmer": kbytes, "ms_per_launch": ms_p1,
+                         "traffic": measured_traffic(kname, per_launch, grid),
+                         "note": ("runscan_kernel reads every entry (8 B key + 2 B count) exactly once; the second kernel "
+                                  "reads candidate records only.  whole_scan = SURVEY §8d's official 22 B/k-mer over T_scan"
+                                  if path == "symm" else "22 B/k-mer = SURVEY §8d (two passes)"),
+                         "whole_scan": {"algorithmic_bytes_per_kmer": ALGO_BYTES_PER_KMER, "achieved": whole,
+                                        "frac": whole / peak, "ms": ms_step}}}
     if multi and job.phase_ms():
         allp = [None] * world
         dist.all_gather_object(allp, {k: round(v, 3) for k, v in job.phase_ms().items()})
-        line["config"]["phases_ms_per_rank"] = allp
+        names = list(allp[0].keys())                                   # one compact list per phase, all ranks
+        line["config"]["phases_ms_by_rank"] = {nm: [a[nm] for a in allp] for nm in names if nm != "-"}
     if e2e is not None:
         line["e2e"] = e2e
+        if multi and "plot_matches_resident_scan" in e2e:
+            parity["e2e_vs_resident"] = bool(e2e["plot_matches_resident_scan"])
+            ok &= parity["e2e_vs_resident"]
     if rank == 0:
         if not args.no_cpu and world == 1:
-            line["cpu_baseline"] = cpu_baseline(args, dev)
+            cb = cpu_baseline(args, dev, keys, cnt, timed_plot)
+            line["cpu_baseline"] = cb["cpu_baseline"]
+            line["e2e_exec"] = cb["e2e_exec"]
+            parity.update(cb["parity"])
+            ok &= all(bool(v) for v in cb["parity"].values())
+        parity["ok"] = bool(ok)
         print(json.dumps(line), flush=True)
     if multi:
         job.close()
+        flag = torch.tensor([int(ok)], dtype=torch.int32, device=dev)
+        dist.broadcast(flag, src=0)
+        ok = bool(flag.item())
         dist.barrier()
         dist.destroy_process_group()
+    if not ok:
+        sys.stderr.write("bench.py: PARITY GATE FAILED -- see the \"parity\" object of the JSON line\n")
+        sys.exit(3)
 
 
-def cpu_baseline(args, dev):
+def cpu_baseline(args, dev, keys, cnt, timed_plot):
+    """The timed table itself as FastK files in /dev/shm: the unmodified reference binary (-T min(cores,64)) and
+    our drop-in executable read the same files.  -> cpu_baseline, e2e_exec (process wall clock of the executable
+    with its own phase breakdown) and the .smu parity flags."""
+    import numpy as np
+    from smudgeplot_b200 import hetmers
+    from tools import synth
     threads = min(host_cores(), 64)
-    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "hetmers")):
-        threads = 1
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "hetmers"))
     d = scratch_dir()
     try:
-        n_s = cpu_sample_size(args, threads)
-        table, nels = make_sample_table(d, n_s, dev)
+        full = have_ref and not os.environ.get("BENCH_CPU_SAMPLE")
+        if full:                                                   # the GPU arm's table, all of it
+            table = os.path.join(d, "table")
+            synth.write_table(table, K, keys, cnt, ibyte=3, nparts=4)
+            nels = int(keys.numel())
+        else:                                                      # scalar port: a bounded sample
+            threads = threads if have_ref else 1
+            table, nels = make_sample_table(d, cpu_sample_size(args, threads), dev)
         secs, kind, smu = time_reference(table, nels, threads, runs=1)
-        # parity while we are here: our executable on the same files must write the same .smu
-        from smudgeplot_b200 import hetmers
+        # our executable on the same files: wall clock of the process (files -> .smu), best of 3
         out = os.path.join(d, "gpu_out")
-        t0 = time.perf_counter()
-        hetmers.run_hetmers(table, o=out, L=LCUT, t=threads)
-        t_gpu = time.perf_counter() - t0
+        env = dict(os.environ, HETMERS_STATS="1")
+        runs = []
+        for _ in range(3):
+            if os.path.exists(out + ".smu"):
+                os.remove(out + ".smu")
+            t0 = time.perf_counter()
+            r = subprocess.run([hetmers.get_binary_path("hetmers"), f"-e{LCUT}", f"-T{threads}", f"-o{out}", table],
+                               input="n\n", capture_output=True, text=True, env=env)
+            dt = time.perf_counter() - t0
+            if r.returncode != 0:
+                raise RuntimeError(f"our hetmers executable failed: {r.stderr[-500:]}")
+            st = None
+            for ln in r.stderr.splitlines():
+                if ln.startswith("{"):
+                    try:
+                        st = json.loads(ln)
+                    except Exception:
+                        pass
+            runs.append((dt, st))
+        best = min(runs, key=lambda x: x[0])
         same = open(out + ".smu").read() == open(smu).read()
-        return {"value": nels / secs[0], "unit": UNIT, "cores": threads, "kind": kind,
-                "sample": f"one run of {'oracle/_ref/hetmers (unmodified reference C)' if kind == 'reference' else 'the oracle port'} "
-                          f"-e{LCUT} -T{threads} on a seeded {nels}-k-mer table of the same workload (4 part files in "
-                          f"{os.path.dirname(table)}, warm page cache), wall clock {secs[0]:.2f} s",
-                "seconds": secs[0], "nels": nels,
-                "our_executable_same_files": {"seconds_wall": t_gpu, "smu_identical": same}}
+        par = {"exec_smu_vs_reference_smu": bool(same)}
+        if full:                                                   # and the timed in-process plot says the same
+            par["timed_plot_vs_reference_smu"] = bool(hetmers.smu_text(timed_plot.cpu().numpy()) == open(smu).read())
+        ref_name = "oracle/_ref/hetmers (unmodified reference C)" if kind == "reference" else "the oracle port"
+        return {"cpu_baseline": {"value": nels / secs[0], "unit": UNIT, "cores": threads, "kind": kind,
+                                 "sample": f"one run of {ref_name} -e{LCUT} -T{threads} on "
+                                           f"{'the timed table itself' if full else 'a seeded sample table of the same workload'}: "
+                                           f"{nels} k-mers, 4 part files in {os.path.dirname(table)} (warm page cache), "
+                                           f"wall clock {secs[0]:.2f} s",
+                                 "seconds": secs[0], "nels": nels},
+                "e2e_exec": {"value": nels / best[0], "unit": UNIT, "seconds_wall": best[0],
+                             "all_runs_s": [round(x[0], 3) for x in runs], "nels": nels, "threads": threads,
+                             "speedup_vs_reference_wall": secs[0] / best[0],
+                             "what": "process wall clock of smudgeplot_b200/bin/hetmers: FastK files in /dev/shm -> .smu "
+                                     "(CUDA start-up, file reads, H2D, unpack, index, scan, .smu write), same files and "
+                                     "-T as the reference run beside it",
+                             "stats": best[1]},
+                "parity": par}
     finally:
         import shutil
         shutil.rmtree(d, ignore_errors=True)

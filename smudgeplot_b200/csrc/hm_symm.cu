@@ -50,7 +50,7 @@
 #define RS_HALO    64                          /* entries staged on either side of the tile      */
 #define RS_WIN     (RS_TILE+2*RS_HALO)
 #define RS_SCANCAP RS_HALO                     /* longest run half scanned linearly               */
-#define RS_STAGE   768                         /* candidate records staged per CTA before they leave */
+#define RS_STAGE   512                         /* candidate records staged per CTA before they leave */
 
 #define SY_STATUS_ASYMMETRIC 1ull              /* a reverse complement was not in the table      */
 #define SY_STATUS_OVERFLOW   2ull              /* candidate list full                             */
@@ -385,6 +385,7 @@ runscan_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ k
 { extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ unsigned s_nc, s_n1, s_n2;
+  __shared__ unsigned s_eq[RS_WIN/32];
   __shared__ unsigned long long s_base;
   RsSmem<KW> S;
   S.key   = (uint64_t *) smem;
@@ -436,39 +437,55 @@ runscan_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ k
   if (mt > 0)
     mbar_wait(&s_bar,0);
 
-  /* ---- classify: singleton / head of a two-entry run / member of a longer run ---- */
-#pragma unroll
-  for (int e = 0; e < RS_EPT; e++)
-    { const int     t = threadIdx.x + e*RS_THREADS;
-      const int     w = t + RS_HALO;
-      const int64_t g = T0+t;
-      bool two = false, more = false;
-      if (g >= lo && g < hi)
-        { const uint64_t x = S.key[w];
-          const bool sp  = (w-1 >= v0) && (((S.key[w-1] ^ x) >> psh) == 0);
-          const bool sn  = (w+1 <  v1) && (((S.key[w+1] ^ x) >> psh) == 0);
-          if (sp | sn)
-            { const bool sp2 = (w-2 >= v0) && (((S.key[w-2] ^ x) >> psh) == 0);
-              const bool sn2 = (w+2 <  v1) && (((S.key[w+2] ^ x) >> psh) == 0);
-              more = (sp && sn) || (sn && sn2) || (sp && sp2);
-              two  = !more && sn;                       /* head of a run of exactly two (the tail stays silent) */
-            }
-        }
-      unsigned bal = __ballot_sync(FULL,two);
-      if (bal != 0)
-        { unsigned base = 0;
-          if (lane == 0) base = atomicAdd(&s_n1,(unsigned) __popc(bal));
-          base = __shfl_sync(FULL,base,0);
-          if (two) S.t1[base + __popc(bal & lt)] = (uint16_t) w;
-        }
-      bal = __ballot_sync(FULL,more);
-      if (bal != 0)
-        { unsigned base = 0;
-          if (lane == 0) base = atomicAdd(&s_n2,(unsigned) __popc(bal));
-          base = __shfl_sync(FULL,base,0);
-          if (more) S.t2[base + __popc(bal & lt)] = (uint16_t) w;
-        }
+  /* ---- adjacency bits: eq[i] = slots i and i+1 hold entries of one run (bit i%32 of word i/32) ---- */
+  const uint64_t pmask = ~(uint64_t) 0 << psh;                    /* the first Pr bases */
+  const int      warp  = threadIdx.x >> 5;
+  for (int wd = warp; wd < RS_WIN/32; wd += RS_THREADS/32)
+    { const int  i  = wd*32 + lane;
+      bool eq = false;
+      if (i >= v0 && i+1 < v1)
+        eq = (((S.key[i] ^ S.key[i+1]) & pmask) == 0);
+      const unsigned bal = __ballot_sync(FULL,eq);
+      if (lane == 0)
+        s_eq[wd] = bal;
     }
+  __syncthreads();
+
+  /* ---- classify 32 entries at a time with bit operations (warp-uniform): head of a run of exactly two
+   *      (its tail stays silent) / member of a longer run / neither                                 ---- */
+  { const int tlo = lo > T0 ? (int) (lo-T0 < RS_TILE ? lo-T0 : RS_TILE) : 0;      /* tile slots of [lo,hi) */
+    const int thi = hi-T0 < RS_TILE ? (int) (hi-T0) : RS_TILE;
+    unsigned m2[RS_EPT], m3[RS_EPT];
+    int      c2 = 0, c3 = 0;
+#pragma unroll
+    for (int e = 0; e < RS_EPT; e++)
+      { const int      wd = RS_HALO/32 + warp*RS_EPT + e;             /* this warp's e-th word of the tile */
+        const unsigned E = s_eq[wd], P = s_eq[wd-1], N = s_eq[wd+1];
+        const unsigned em1 = (E << 1) | (P >> 31);                     /* eq[w-1] */
+        const unsigned em2 = (E << 2) | (P >> 30);                     /* eq[w-2] */
+        const unsigned ep1 = (E >> 1) | (N << 31);                     /* eq[w+1] */
+        const int      t0  = (wd - RS_HALO/32)*32;                     /* tile slot of bit 0 */
+        unsigned act = 0xffffffffu;
+        if (t0 < tlo)      act &= (tlo-t0 >= 32) ? 0u : (0xffffffffu << (tlo-t0));
+        if (t0+32 > thi)   act &= (thi-t0 <= 0)  ? 0u : (0xffffffffu >> (t0+32-thi));
+        m3[e] = ((em1 & E) | (E & ep1) | (em1 & em2)) & act;
+        m2[e] = (E & ~em1 & ~ep1) & act;
+        c2 += __popc(m2[e]); c3 += __popc(m3[e]);
+      }
+    unsigned b2 = 0, b3 = 0;
+    if (lane == 0)
+      { if (c2 > 0) b2 = atomicAdd(&s_n1,(unsigned) c2);
+        if (c3 > 0) b3 = atomicAdd(&s_n2,(unsigned) c3);
+      }
+    b2 = __shfl_sync(FULL,b2,0); b3 = __shfl_sync(FULL,b3,0);
+#pragma unroll
+    for (int e = 0; e < RS_EPT; e++)
+      { const int w = (RS_HALO/32 + warp*RS_EPT + e)*32 + lane;
+        if ((m2[e] >> lane) & 1) S.t1[b2 + __popc(m2[e] & lt)] = (uint16_t) w;
+        if ((m3[e] >> lane) & 1) S.t2[b3 + __popc(m3[e] & lt)] = (uint16_t) w;
+        b2 += __popc(m2[e]); b3 += __popc(m3[e]);
+      }
+  }
   __syncthreads();
 
   /* ---- runs of two: one comparison settles both members ---- */

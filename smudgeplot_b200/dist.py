@@ -139,6 +139,73 @@ def balanced_offsets(keys_full: torch.Tensor, world: int, depth: int = 3, per_ca
     return offs + [n]
 
 
+def run_aligned_cuts(keys_full: torch.Tensor, kmer: int, world: int):
+    """Shard cuts of the strand-symmetric scan: equal entry counts, each cut moved to the next RUN
+    boundary (a run = entries sharing their first k/2 bases; all partners the run scan looks for lie in
+    one run, so no pair straddles two shards).  Pure torch: every rank computes the same cuts from its
+    replica.  -> [0, c1, ..., n]"""
+    n = keys_full.numel()
+    sh = 64 - 2 * (kmer >> 1)
+
+    def pre(t):                                   # first k/2 bases as a non-negative number
+        return (t >> sh) & ((1 << (64 - sh)) - 1) if sh > 0 else t
+
+    cuts = [0]
+    for r in range(1, world):
+        c = max((n * r) // world, cuts[-1])
+        if 0 < c < n:
+            p0 = pre(keys_full[c - 1:c])
+            while c < n:
+                w = keys_full[c:c + 65536]
+                d = torch.nonzero(pre(w) != p0)
+                if d.numel():
+                    c += int(d[0])
+                    break
+                c += w.numel()
+        cuts.append(min(c, n))
+    return cuts + [n]
+
+
+def fingerprint_verdict(acc: torch.Tensor, group=None) -> bool:
+    """acc = this rank's int64[4] fingerprint sums (device.DeviceTable.fingerprint over the entries it
+    loaded, same seeds on every rank): symmetric iff the job-wide sums (mod 2^64) of {(x,cnt)} and
+    {(rc x,cnt)} agree"""
+    world = dist.get_world_size(group)
+    parts = [torch.zeros_like(acc) for _ in range(world)]
+    dist.all_gather(parts, acc, group=group)
+    tot = [0, 0, 0, 0]
+    for p in parts:
+        for i, v in enumerate(p.tolist()):
+            tot[i] = (tot[i] + v) & 0xFFFFFFFFFFFFFFFF
+    return tot[0] == tot[2] and tot[1] == tot[3]
+
+
+def common_seeds(device, group=None):
+    """rank 0's fingerprint seeds for everybody"""
+    import ctypes as C
+    from . import _lib
+    sd = (C.c_uint64 * 2)()
+    _lib.lib().hm_symm_seeds(sd)
+    t = torch.tensor([sd[0] - (1 << 64) if sd[0] >= (1 << 63) else sd[0],
+                      sd[1] - (1 << 64) if sd[1] >= (1 << 63) else sd[1]], dtype=torch.int64, device=device)
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    dist.broadcast(t, src=src, group=group)
+    return [int(v) & 0xFFFFFFFFFFFFFFFF for v in t.tolist()]
+
+
+def exchange_segments(seg: torch.Tensor, rank: int, group=None):
+    """seg[world, m]: row `rank` is this rank's Bloom segment; fill in everybody else's (all-gather)"""
+    own = seg[rank].clone()
+    try:
+        dist.all_gather_into_tensor(seg.view(-1), own, group=group)
+    except (RuntimeError, NotImplementedError):
+        parts = [torch.empty_like(own) for _ in range(seg.shape[0])]
+        dist.all_gather(parts, own, group=group)
+        for r, p in enumerate(parts):
+            seg[r].copy_(p)
+    return seg
+
+
 class PeerDeg:
     """The sharded incidence array of DESIGN.md §6 for a one-process-per-GPU job: every rank
     cudaMallocs its own full-length array through the C ABI (hm_dev_alloc), exports a CUDA IPC
@@ -226,29 +293,52 @@ class PeerDeg:
 class ShardedScan:
     """device-resident replica + this rank's work range; `scan()` = T_scan of SURVEY.md §8d"""
 
-    def __init__(self, kmer, keys_full, cnt_full, lo, hi, group=None, keys_lo_full=None):
+    def __init__(self, kmer, keys_full, cnt_full, lo, hi, group=None, keys_lo_full=None, path="auto"):
+        import os
         from .device import DeviceTable
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        self.table = DeviceTable(kmer, keys_full, cnt_full, keys_lo=keys_lo_full).build_index()
+        self.table = DeviceTable(kmer, keys_full, cnt_full, keys_lo=keys_lo_full).build_index(direct=False)
         self.load_lo, self.load_hi = lo, hi       # the shard this rank LOADED (equal prefix ranges)
+        self.kmer = kmer
+        self.n_total = keys_full.numel()
+        self.bits = self.table.bits
+        self.peer = None
+        # is the whole table strand-symmetric?  every rank fingerprints the shard it loaded
+        path = os.environ.get("HETMERS_PATH", path)
+        self.seeds = common_seeds(keys_full.device, group)
+        self.symmetric = kmer >= 2 and fingerprint_verdict(self.table.fingerprint(lo, hi, self.seeds), group)
+        self.table.symmetric = self.symmetric
+        self.path = "symm" if (self.symmetric and path != "direct") else "direct"
+        if self.path == "symm":
+            # strand-symmetric scan: run-aligned shards of equal size, Bloom segments all-gathered
+            self.offsets = run_aligned_cuts(keys_full, kmer, self.world)
+            lo, hi = self.offsets[self.rank], self.offsets[self.rank + 1]
+            self.table.alloc_symm(lo, hi, self.table.make_symm_shards(self.offsets, self.rank) if self.world > 1 else None)
+            self.lo, self.hi = lo, hi
+            self.exchange = "all-gather of Bloom segments (NCCL) between run scan and resolve" if self.world > 1 else "none"
+        else:
+            self._init_direct(keys_full)
+        self._barrier_t = torch.zeros(1, dtype=torch.int32, device=keys_full.device)
+        self._step = 0
+        if keys_full.is_cuda:
+            self._side = torch.cuda.Stream(device=keys_full.device)
+        if self.peer is not None:       # tensors over the two halves of the IPC allocation (no ownership)
+            self._peer_views = [_cuda_view(self.peer.own + h * self.peer.nbytes, self.peer.nbytes, keys_full.device)
+                                for h in (0, 1)]
+
+    def _init_direct(self, keys_full):
+        """direct passes (any table): work-balanced shards, incidence array sharded by owner"""
+        self.table.build_filter()
         # the shard this rank SCANS and owns the incidence bytes of: equal work, not equal counts
         self.offsets = balanced_offsets(keys_full, self.world)
         lo, hi = self.offsets[self.rank], self.offsets[self.rank + 1]
         self.table.alloc_work(lo, hi)
-        self.kmer, self.lo, self.hi = kmer, lo, hi
-        self.n_total = keys_full.numel()
-        self.bits = self.table.bits
-        self.peer = PeerDeg.create(self.n_total, keys_full.device, group) if self.world > 1 else None
+        self.lo, self.hi = lo, hi
+        self.peer = PeerDeg.create(self.n_total, keys_full.device, self.group) if self.world > 1 else None
         self.exchange = "peer-memory (remote atomics/loads over NVLink, CUDA IPC)" if self.peer else \
                         ("all-reduce(uint8[n]) via NCCL" if self.world > 1 else "none")
-        self._barrier_t = torch.zeros(1, dtype=torch.int32, device=keys_full.device)
-        self._step = 0
-        self._side = torch.cuda.Stream(device=keys_full.device)
-        if self.peer is not None:       # tensors over the two halves of the IPC allocation (no ownership)
-            self._peer_views = [_cuda_view(self.peer.own + h * self.peer.nbytes, self.peer.nbytes, keys_full.device)
-                                for h in (0, 1)]
 
     @classmethod
     def from_synthetic(cls, k, G, ploidy, het, cov, L, seed, device, group=None):
@@ -287,6 +377,8 @@ class ShardedScan:
         pass 2 of scan s-1 (it could not have passed that scan's plot all-reduce otherwise), and
         nobody writes it before the plot all-reduce of scan s, which the clearing rank joins only
         after its memset (stream order)."""
+        if self.path == "symm":
+            return self._scan_symm(t, events)
         if self.peer is None:
             t.deg.zero_()
             t.plot.zero_()
@@ -333,6 +425,38 @@ class ShardedScan:
         if ph: ph[5].record()
         return t.plot
 
+    def _scan_symm(self, t, events=None):
+        """strand-symmetric scan, sharded: run scan of the own (run-aligned) range -> all-gather of the
+        Bloom segments -> resolve of the own candidates -> plot all-reduce.  No peer memory needed."""
+        ph = self._phase_events() if self.profile_phases else None
+        t.plot.zero_()
+        if events is not None:
+            events[0].record()
+        if ph: ph[0].record()
+        t.runscan()
+        if events is not None:
+            events[1].record()
+        if ph: ph[1].record()
+        if self.world > 1:
+            exchange_segments(t.bloom_view(), self.rank, self.group)
+        if ph: ph[2].record()
+        t.resolve()
+        if ph: ph[3].record(); ph[4].record()
+        if self.world > 1:
+            allreduce_plot(t.plot, self.group)
+        if ph: ph[5].record()
+        return t.plot
+
+    def symm_ok(self) -> bool:
+        """status words of the last symmetric scan on every rank (synchronises): all clean?"""
+        bad = torch.zeros(1, dtype=torch.int32, device=self.table.device)
+        if self.path == "symm":
+            _, st = self.table.symm_status()
+            bad[0] = int(st != 0)
+        if self.world > 1:
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=self.group)
+        return int(bad.item()) == 0
+
     profile_phases = False
 
     def _phase_events(self):
@@ -347,7 +471,8 @@ class ShardedScan:
         rows = [[a.elapsed_time(b) for a, b in zip(ev[:-1], ev[1:])] for ev in getattr(self, "_phases", [])]
         if not rows:
             return None
-        names = ["pass1", "barrier_after_pass1", "pass2", "zero_next_buffer", "plot_allreduce"]
+        names = ["pass1", "barrier_after_pass1", "pass2", "zero_next_buffer", "plot_allreduce"] if self.path != "symm" else \
+                ["runscan", "bloom_allgather", "resolve", "-", "plot_allreduce"]
         return {n: sum(r[i] for r in rows) / len(rows) for i, n in enumerate(names)}
 
     # ---- end-to-end from pinned host buffers (bench.py e2e leg) -----------------------------
@@ -388,8 +513,14 @@ class ShardedScan:
             d_idx.copy_(h_idx, non_blocking=True)
             DeviceTable.from_records(k, ibyte, d_rec, d_idx, first=lo, out=(k2, c2))
             gather_table(k2[lo:hi], c2[lo:hi], self.group, out=(k2, c2))
-            tt = DeviceTable(k, k2, c2, bits=self.bits).build_index()
-            tt.alloc_work(wlo, whi)
+            tt = DeviceTable(k, k2, c2, bits=self.bits).build_index(direct=(self.path != "symm"))
+            if self.path == "symm":
+                # (the fingerprint of the freshly unpacked shard is part of the timed call)
+                if not fingerprint_verdict(tt.fingerprint(lo, hi, self.seeds), self.group):
+                    raise RuntimeError("e2e replica is not symmetric although the resident table was")
+                tt.alloc_symm(wlo, whi, self.table.symm_shards)
+            else:
+                tt.alloc_work(wlo, whi)
             self.scan_on(tt)
             if self.rank == 0:
                 h_plot.copy_(tt.plot, non_blocking=True)
@@ -412,6 +543,8 @@ class ShardedScan:
         return {"value": n / dtv, "unit": "k-mers/s", "ms_per_step": dtv * 1e3,
                 "h2d_bytes_per_step": int(h2d.item()),
                 "d2h_bytes_per_step": int(_lib.PLOT_CELLS * 8),
-                "api": "smudgeplot_b200.dist: pinned shard records -> H2D -> hm_k_unpack_records -> shard broadcast "
-                       "(NCCL) -> hm_k_build_bucket_index -> pass1 -> all-reduce(deg) -> pass2 -> all-reduce(plot) -> D2H",
+                "api": "smudgeplot_b200.dist: pinned shard records -> H2D -> hm_k_unpack_records -> shard exchange "
+                       "(NCCL) -> hm_k_build_bucket_index -> " +
+                       ("fingerprint -> runscan -> all-gather(Bloom) -> resolve" if self.path == "symm" else
+                        "filter -> pass1 -> deg exchange -> pass2") + " -> all-reduce(plot) -> D2H",
                 "plot_matches_resident_scan": same, "exchange": self.exchange}

@@ -429,11 +429,12 @@ int main(int argc, char *argv[])
   hm_table_close(T);
 
   if (getenv("HETMERS_STATS") != NULL)
-    fprintf(stderr,"{\"nels\": %lld, \"n_gpus\": %d, \"bucket_bits\": %d, \"ms_load\": %.3f, "
+    fprintf(stderr,"{\"nels\": %lld, \"n_gpus\": %d, \"path\": \"%s\", \"bucket_bits\": %d, \"ms_load\": %.3f, "
                    "\"ms_pass1\": %.3f, \"ms_pass2\": %.3f, \"ms_scan\": %.3f, \"kernel_launches\": %lld, "
                    "\"wall_ms\": {\"open\": %.1f, \"cuda_init_load\": %.1f, \"examine\": %.1f, \"scan\": %.1f}, "
                    "\"load_ms\": {\"alloc\": %.1f, \"records\": %.1f, \"index\": %.1f}}\n",
-            (long long) stats.nels,stats.n_gpus,stats.bucket_bits,stats.ms_h2d_unpack,
+            (long long) stats.nels,stats.n_gpus,stats.path == HM_PATH_SYMM ? "symmetric" : "direct",
+            stats.bucket_bits,stats.ms_h2d_unpack,
             stats.ms_pass1,stats.ms_pass2,stats.ms_scan,(long long) stats.kernel_launches,
             t_open-t_start,t_load-t_open,t_exam-t_load,t_scan-t_exam,
             stats.ms_alloc,stats.ms_records,stats.ms_index);

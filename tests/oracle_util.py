@@ -155,3 +155,78 @@ def partial_pass2(cnt: np.ndarray, deg: np.ndarray, up: np.ndarray, lo: int, hi:
             ci, cj = int(cnt[i]), int(cnt[j])
             plot[ci + cj, min(ci, cj)] += 1
     return plot
+
+
+# ---- the strand-symmetric scan's two kernels, restated (multi-GPU host-logic tests; k <= 32) ----
+
+def _rc(x: int, k: int) -> int:
+    r = 0
+    v = x >> (64 - 2 * k)
+    for _ in range(k):
+        r = (r << 2) | (3 - (v & 3))
+        v >>= 2
+    return r << (64 - 2 * k)
+
+
+def partial_runscan(keys_u64: np.ndarray, cnt: np.ndarray, k: int, lo: int, hi: int, seg_bits: int):
+    """what hm_k_symm_runscan leaves for the run-aligned range [lo,hi): a membership segment over the
+    entries with a partner at a position >= k - k/2 (here an exact bitmap hashed by key % seg_bits, so
+    that false positives exist as in the Bloom filter) and the candidate records (x, cx, cy, pos, yb)."""
+    pos_of = {int(x): i for i, x in enumerate(keys_u64.tolist())}
+    Pr, pup = k // 2, k - k // 2
+    seg = np.zeros(seg_bits, dtype=np.uint8)
+
+    def partners(i, p0):
+        x, cx, out = int(keys_u64[i]), int(cnt[i]), []
+        for p in range(p0, k):
+            sh = 62 - 2 * p
+            b = (x >> sh) & 3
+            for alt in range(4):
+                if alt != b:
+                    j = pos_of.get((x & ~(3 << sh)) | (alt << sh))
+                    if j is not None and cx + int(cnt[j]) <= SMAX:
+                        out.append((j, p))
+        return out
+
+    cand = []
+    for i in range(lo, hi):
+        pr = partners(i, Pr)
+        if any(p >= pup for _, p in pr):
+            seg[int(keys_u64[i]) % seg_bits] = 1
+        if len(pr) == 1 and pr[0][0] > i and len(partners(pr[0][0], Pr)) == 1:
+            j, p = pr[0]
+            cand.append((int(keys_u64[i]), int(cnt[i]), int(cnt[j]), p, (int(keys_u64[j]) >> (62 - 2 * p)) & 3))
+    return seg, cand
+
+
+def partial_resolve(keys_u64: np.ndarray, cnt: np.ndarray, k: int, cand, segs, first_keys):
+    """what hm_k_symm_resolve adds for one shard's candidates given ALL shards' segments: a Bloom hit is
+    settled exactly on the replica; isolated pairs count once, or twice when the mirror pair is another"""
+    pos_of = {int(x): i for i, x in enumerate(keys_u64.tolist())}
+    pup = k - k // 2
+    plot = np.zeros((SMAX + 1, PLOT_W), dtype=np.int64)
+
+    def in_S(q):
+        owner = sum(1 for f in first_keys[1:] if q >= f)
+        if not segs[owner][q % len(segs[owner])]:
+            return False
+        i = pos_of[q]
+        cq = int(cnt[i])
+        for p in range(pup, k):
+            sh = 62 - 2 * p
+            b = (q >> sh) & 3
+            for alt in range(4):
+                if alt != b:
+                    j = pos_of.get((q & ~(3 << sh)) | (alt << sh))
+                    if j is not None and cq + int(cnt[j]) <= SMAX:
+                        return True
+        return False
+
+    for x, cx, cy, p, yb in cand:
+        rx = _rc(x, k)
+        sh = 62 - 2 * (k - 1 - p)
+        ry = (rx & ~(3 << sh)) | ((3 - yb) << sh)
+        if in_S(rx) or in_S(ry):
+            continue
+        plot[cx + cy, min(cx, cy)] += 1 if 2 * p == k - 1 else 2
+    return plot

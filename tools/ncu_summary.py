@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Summarise an .ncu-rep (read here, no GPU): headline metrics and a per-source-line breakdown.
-usage: python tools/ncu_summary.py <report.ncu-rep> [mangled-kernel-substring]"""
+usage: python tools/ncu_summary.py <report.ncu-rep> [mangled-kernel-substring [demangled-name-substring]]"""
 import csv
 import io
 import re
@@ -64,7 +64,16 @@ def main():
         if mm:
             off2line[int(mm.group(1), 16)] = cur
     rows = list(csv.reader(io.StringIO(run('ncu', '-i', rep, '--page', 'source', '--csv'))))
-    hdr, data = rows[1], rows[2:]
+    # one section per profiled launch ("Kernel Name" row, header row, instruction rows): take the first
+    # section whose kernel name matches the demangled form of `sub` (or simply the first one)
+    starts = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name'] + [len(rows)]
+    want = sys.argv[3] if len(sys.argv) > 3 else None
+    sec = 0
+    for k in range(len(starts) - 1):
+        if want and want in rows[starts[k]][1]:
+            sec = k
+            break
+    hdr, data = rows[starts[sec] + 1], rows[starts[sec] + 2:starts[sec + 1]]
     ia, ii, isamp = hdr.index('Address'), hdr.index('Instructions Executed'), hdr.index('# Samples')
     base = int(data[0][ia], 16)
     agg = defaultdict(lambda: [0, 0, 0])
@@ -82,7 +91,7 @@ def main():
                 for cand in glob.glob(os.path.join(root, 'smudgeplot_b200/csrc', ln[0])):
                     srcs[ln[0]] = open(cand).read().splitlines()
             text = srcs.get(ln[0], [''] * (ln[1] + 1))[ln[1] - 1].strip()[:88]
-        print(f'  {str(ln[1] if ln else None):>5s}: sass {c:4d}  inst {100 * i / ti:5.1f}%  stalls {100 * s / ts:5.1f}%  {text}')
+        print(f'  {(ln[0][:14] + ":" + str(ln[1])) if ln else "None":>20s}: sass {c:4d}  inst {100 * i / ti:5.1f}%  stalls {100 * s / ts:5.1f}%  {text}')
 
 
 if __name__ == '__main__':
