@@ -257,6 +257,10 @@ typedef struct hm_scan hm_scan;   /* opaque: device-resident table + work buffer
  * work is sharded by contiguous index range).  Replaces Open_Kmer_Stream +
  * Clone_Kmer_Stream + the 4 GiB cache fill (libfastk.c:786-951; PloidyPlot.c:954-964).       */
 int  hm_scan_create(const hm_host_table *t, const int *dev, int n_gpus, hm_scan **out);
+/* Optional: start CUDA (driver + primary contexts of the first n_gpus visible devices, 0 = all) and
+ * the pinned staging buffers on a background thread and return at once; hm_scan_create waits for
+ * it.  Lets a short-lived process overlap CUDA start-up with opening its table files.             */
+void hm_prewarm(int n_gpus);
 /* host threads used to stage pageable (e.g. mmap'ed) part payloads into pinned memory during
  * hm_scan_create; 0 = min(16, cores).  The executable passes its -T here.                      */
 void hm_set_io_threads(int n);

@@ -137,7 +137,7 @@ static void free_dev(DevTable *D)
   dfree(D->dev,D->st,D->up);    dfree(D->dev,D->st,D->plot);
   dfree(D->dev,D->st,D->fp_acc);
   if (D->p2scratch) cudaFree(D->p2scratch);
-  if (D->symm_work) cudaFree(D->symm_work);
+  dfree(D->dev,D->st,D->symm_work);
   if (D->st) cudaStreamSynchronize(D->st);
   if (D->st)      cudaStreamDestroy(D->st);
   if (D->st_copy) cudaStreamDestroy(D->st_copy);
@@ -219,6 +219,43 @@ static int parallel_fill(uint8_t *dst, const uint8_t *src, int fd, int64_t foff,
   return err;
 }
 
+/* ---- background start-up (hm_prewarm) ---- */
+#define PIN_CACHE_BYTES ((size_t) (LOAD_CHUNK/2) * 8)
+static pthread_t g_warm_th;
+static int       g_warm_state = 0;            /* 0 idle, 1 running, 2 joined */
+static int       g_warm_ngpu = 1;
+static uint8_t  *g_pin_cache[2] = { NULL, NULL };
+
+static void *warm_worker(void *)
+{ int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess)
+    { cudaGetLastError(); return NULL; }
+  int use = (g_warm_ngpu <= 0 || g_warm_ngpu > n) ? n : g_warm_ngpu;
+  for (int g = 0; g < use; g++)
+    if (cudaSetDevice(g) == cudaSuccess)
+      cudaFree(0);                            /* creates the primary context */
+  cudaSetDevice(0);
+  for (int i = 0; i < 2; i++)
+    if (cudaHostAlloc(&g_pin_cache[i],PIN_CACHE_BYTES,cudaHostAllocDefault) != cudaSuccess)
+      { cudaGetLastError(); g_pin_cache[i] = NULL; }
+  return NULL;
+}
+
+extern "C" void hm_prewarm(int n_gpus)
+{ if (g_warm_state != 0)
+    return;
+  g_warm_ngpu = n_gpus;
+  if (pthread_create(&g_warm_th,NULL,warm_worker,NULL) == 0)
+    g_warm_state = 1;
+}
+
+static void prewarm_join(void)
+{ if (g_warm_state == 1)
+    { pthread_join(g_warm_th,NULL);
+      g_warm_state = 2;
+    }
+}
+
 static int is_pageable(const void *p)
 { cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a,p) != cudaSuccess)
@@ -250,10 +287,15 @@ static int load_range(hm_scan *s, DevTable *D, const hm_host_table *t, const int
   if (staged)
     chunk = LOAD_CHUNK/2;
   if (chunk > count) chunk = count;
+  int pin_cached[2] = {0,0};
   for (int i = 0; i < 2; i++)
     { HM_CUDA(dalloc(D->dev,D->st,(void **) &stage[i],(size_t) chunk*pbyte));
       if (staged)
-        HM_CUDA(cudaHostAlloc(&pin[i],(size_t) chunk*pbyte,cudaHostAllocDefault));
+        { if (s->ngpu == 1 && g_pin_cache[i] != NULL && (size_t) chunk*pbyte <= PIN_CACHE_BYTES)
+            { pin[i] = g_pin_cache[i]; g_pin_cache[i] = NULL; pin_cached[i] = 1; }   /* from hm_prewarm */
+          else
+            HM_CUDA(cudaHostAlloc(&pin[i],(size_t) chunk*pbyte,cudaHostAllocDefault));
+        }
       HM_CUDA(cudaEventCreateWithFlags(&copied[i],cudaEventDisableTiming));
       HM_CUDA(cudaEventCreateWithFlags(&unpacked[i],cudaEventDisableTiming));
     }
@@ -311,7 +353,10 @@ static int load_range(hm_scan *s, DevTable *D, const hm_host_table *t, const int
   cudaError_t e = cudaStreamSynchronize(D->st);
   for (int i = 0; i < 2; i++)
     { dfree(D->dev,D->st,stage[i]); cudaEventDestroy(copied[i]); cudaEventDestroy(unpacked[i]);
-      if (pin[i] != NULL) cudaFreeHost(pin[i]);
+      if (pin[i] != NULL)
+        { if (pin_cached[i]) g_pin_cache[i] = pin[i];        /* back into the cache for the next table */
+          else               cudaFreeHost(pin[i]);
+        }
     }
   if (rc == HM_OK && e != cudaSuccess)
     rc = hm_cuda_fail(e,"unpack");
@@ -369,6 +414,7 @@ extern "C" int hm_scan_create(const hm_host_table *t, const int *dev, int n_gpus
   int kbyte = (t->kmer+3)>>2;
   if (t->ibyte < 1 || t->ibyte > 3 || t->ibyte > kbyte)
     return hm_set_error(HM_EFORMAT,"table has ibyte=%d with k=%d",t->ibyte,t->kmer);
+  prewarm_join();
   if (hm_device_count() < 1)
     return hm_set_error(HM_ECUDA,"no CUDA device visible (this build has no CPU fallback)");
 
@@ -532,8 +578,8 @@ static int ensure_symm(hm_scan *s)
       D->slo = cut[g]; D->shi = cut[g+1];
       int rc = hm_symm_plan(n,D->shi-D->slo,s->kmer,G,&D->symm_layout);
       if (rc != HM_OK) return rc;
-      if (D->symm_work != NULL) { cudaFree(D->symm_work); D->symm_work = NULL; }
-      HM_CUDA(cudaMalloc(&D->symm_work,(size_t) D->symm_layout.bytes));
+      if (D->symm_work != NULL) { dfree(D->dev,D->st,D->symm_work); D->symm_work = NULL; }
+      HM_CUDA(dalloc(D->dev,D->st,&D->symm_work,(size_t) D->symm_layout.bytes));
     }
   s->have_symm = 1;
   return HM_OK;
@@ -562,7 +608,7 @@ extern "C" int hm_scan_condition(hm_scan *s, int ethresh, int do_trim, int do_sy
       dfree(D->dev,D->st,D->up);     D->up = NULL;
       dfree(D->dev,D->st,D->bucket); D->bucket = NULL;
       dfree(D->dev,D->st,D->filter); D->filter = NULL;
-      if (D->symm_work != NULL) { cudaFree(D->symm_work); D->symm_work = NULL; }
+      if (D->symm_work != NULL) { dfree(D->dev,D->st,D->symm_work); D->symm_work = NULL; }
       /* the table arrays are about to be replaced by plain cudaMalloc'ed ones: hand pooled ones back
        * (conditioning frees them with cudaFree, which is legal for pool memory)                    */
       PoolReg *R = g_pool + (D->dev < 64 ? D->dev : 0);

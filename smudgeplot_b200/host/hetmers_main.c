@@ -16,6 +16,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 #include <strings.h>
 
 #include <time.h>
@@ -145,6 +146,46 @@ static void read_sma(const char *arg, const char *out_root, uint16_t *pixmap, Sm
 }
 
 #endif
+
+/* How many GPUs HETMERS_GPUS asks for (0 = "all").  Called before the first CUDA call: a process
+ * that will use g GPUs of an 8-GPU box need not pay for the driver initialising the other 8-g, so
+ * CUDA_VISIBLE_DEVICES is narrowed to the first g visible devices, and CUDA start-up (driver +
+ * context creation, ~0.5 s) then runs on a background thread while the table files are opened.  */
+static int wanted_gpus(void)
+{ const char *g = getenv("HETMERS_GPUS");
+  int n = 1;
+  if (g != NULL && *g != '\0')
+    { if (strcasecmp(g,"all") == 0)
+        return 0;
+      n = atoi(g);
+      if (n < 1) n = 1;
+      if (n > 16) n = 16;
+    }
+  return n;
+}
+
+static void start_cuda_early(void)
+{ int   want = wanted_gpus(), i;
+  const char *vis = getenv("CUDA_VISIBLE_DEVICES");
+  if (want > 0)
+    { char buf[512];
+      if (vis == NULL || *vis == '\0')
+        { char *o = buf;
+          for (i = 0; i < want; i++)
+            o += sprintf(o,i ? ",%d" : "%d",i);
+          setenv("CUDA_VISIBLE_DEVICES",buf,1);
+        }
+      else if (strlen(vis) < sizeof(buf))
+        { int commas = 0;
+          strcpy(buf,vis);
+          for (i = 0; buf[i] != '\0'; i++)
+            if (buf[i] == ',' && ++commas == want)
+              { buf[i] = '\0'; break; }
+          setenv("CUDA_VISIBLE_DEVICES",buf,1);
+        }
+    }
+  hm_prewarm(want);
+}
 
 static int pick_gpus(int *devs)
 { int ngpu = 1, navail = hm_device_count(), i;
@@ -293,6 +334,8 @@ int main(int argc, char *argv[])
   int       ngpu, devs[16];
   double    t_start = wall_ms(), t_open, t_load, t_exam, t_scan;
 
+  start_cuda_early();            /* background: nothing below waits for it before hm_device_count() */
+
   { char *command, *tname;
     int   symm, trim;
 
@@ -425,8 +468,8 @@ int main(int argc, char *argv[])
   if (hm_scan_extract(S,PIXMAP,&REC,&NREC) != HM_OK)
     die_hm();
 #endif
-  hm_scan_destroy(S);
-  hm_table_close(T);
+  //  (the device-resident table is not torn down: the process is about to end, and destroying the CUDA
+  //   context by hand costs ~0.1 s of wall clock for nothing)
 
   if (getenv("HETMERS_STATS") != NULL)
     fprintf(stderr,"{\"nels\": %lld, \"n_gpus\": %d, \"path\": \"%s\", \"bucket_bits\": %d, \"ms_load\": %.3f, "
@@ -492,5 +535,6 @@ int main(int argc, char *argv[])
 
   free(PLOT);
   free(OUT);
-  exit (0);
+  fflush(NULL);
+  _exit (0);                     /* exit(0) without the CUDA runtime's atexit teardown */
 }

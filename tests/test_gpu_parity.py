@@ -307,7 +307,7 @@ def test_result_independent_of_bucket_bits_and_work_split():
     ref = None
     for bits, fbits in ((2, 22), (9, 23), (15, 26), (20, 29), (17, 31), (17, 32), (12, 33), (17, 34), (16, 35), (17, 36), (17, 37)):
         t = DeviceTable(25, keys, c16, bits=bits, fbits=fbits).build_index()
-        p = t.scan().clone()
+        p = t.scan("direct").clone()
         ref = p if ref is None else ref
         assert torch.equal(p, ref), (bits, fbits)
         del t
@@ -345,7 +345,7 @@ def test_64bit_offset_kernels_match_32bit(k):
     c16 = cnt.to(torch.int16)
     a = DeviceTable(k, khi, c16, keys_lo=klo).build_index()
     b = DeviceTable(k, khi, c16, keys_lo=klo, force_idx64=True).build_index()
-    pa, pb = a.scan().clone(), b.scan().clone()
+    pa, pb = a.scan("direct").clone(), b.scan("direct").clone()
     assert b.up.dtype == torch.int64 and b.bucket.dtype == torch.int64
     assert torch.equal(pa, pb) and int(pa.sum()) > 0
     assert torch.equal(a.deg[:a.n], b.deg[:b.n])
@@ -365,7 +365,7 @@ def test_long_kmer_work_split_and_filter_widths():
     ref = None
     for bits, fbits in ((3, 22), (14, 27), (16, 32), (15, 35), (16, 37)):
         t = DeviceTable(40, khi, c16, bits=bits, fbits=fbits, keys_lo=klo).build_index()
-        p = t.scan().clone()
+        p = t.scan("direct").clone()
         ref = p if ref is None else ref
         assert torch.equal(p, ref), (bits, fbits)
     n = khi.numel()
@@ -437,10 +437,13 @@ def test_full_size_properties_config2():
     n = keys.numel()
     assert abs(n - 2e8) < 2e7
     t = DeviceTable(k, keys, cnt.to(torch.int16)).build_index()
-    plot = t.scan().clone()
+    plot = t.scan("direct").clone()
     deg = t.deg[:n].clone()
-    plot_again = t.scan()
+    plot_again = t.scan("direct")
     assert torch.equal(plot, plot_again)
+    assert t.check_symmetric()
+    assert torch.equal(t.scan("symm"), plot)          # the strand-symmetric scan: same plot, twice
+    assert torch.equal(t.scan("symm"), plot)
     rc = synth.revcomp_left(keys, k)
     pos = t.find(rc)
     assert bool((pos >= 0).all())
@@ -456,18 +459,21 @@ def test_full_size_properties_config2():
 
 # ------------------------------------------------------------------ multi-GPU (one process) ---
 
+@pytest.mark.parametrize("path", ["symm", "direct"])
 @pytest.mark.parametrize("ngpu", [2, 4, 8])
-def test_multi_gpu_single_process_matches_single_gpu(ngpu, tmp_path):
-    """HETMERS_GPUS=n: shards unpacked per GPU, gathered by peer copies, degree bytes summed by the
-    peer-memory kernel (csrc/hm_peer.cu), plots reduced onto GPU 0 -- same .smu as one GPU."""
+def test_multi_gpu_single_process_matches_single_gpu(ngpu, path, tmp_path, monkeypatch):
+    """HETMERS_GPUS=n: shards unpacked per GPU (one host thread each), gathered by peer copies; symmetric
+    scan: Bloom segments exchanged by peer copies; direct passes: degree bytes reached through the owner's
+    array (csrc/hm_peer.cu for the dense fall-back); plots reduced onto GPU 0 -- same .smu as one GPU."""
     if _lib.lib().hm_device_count() < ngpu:
         pytest.skip(f"needs {ngpu} GPUs")
+    monkeypatch.setenv("HETMERS_PATH", path)
     keys, cnt = synth.synth_table(31, 400000, 3, 0.01, 60, 12, 4, device="cuda")
     name = str(tmp_path / "t")
     kt = synth.write_table(name, 31, keys, cnt, ibyte=3, nparts=3)
     one, _ = hetmers.scan_table(kt, gpus=1)
     many, st = hetmers.scan_table(kt, gpus=ngpu)
-    assert st["n_gpus"] == ngpu
+    assert st["n_gpus"] == ngpu and st["path"] == (2 if path == "symm" else 1)
     assert np.array_equal(one, many)
     out = str(tmp_path / "o")
     hetmers.run_hetmers(name, o=out, L=12, t=4, gpus=ngpu)
@@ -490,15 +496,16 @@ def test_multi_gpu_dense_exchange_fallback(tmp_path, monkeypatch):
     keys, cnt = synth.synth_table(27, 300000, 2, 0.02, 40, 6, 9, device="cuda")
     kt = synth.write_table(str(tmp_path / "t"), 27, keys, cnt, ibyte=3, nparts=2)
     one, _ = hetmers.scan_table(kt, gpus=1)
+    monkeypatch.setenv("HETMERS_PATH", "direct")
     monkeypatch.setenv("HETMERS_DENSE_EXCHANGE", "1")
     many, _ = hetmers.scan_table(kt, gpus=2)
     assert np.array_equal(one, many)
 
 
-def _dist_worker(rank, world, port, q, dense):
+def _dist_worker(rank, world, port, q, dense, path="direct"):
     import torch
     import torch.distributed as dist
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), HETMERS_PATH=path)
     if dense:
         os.environ["HETMERS_DENSE_EXCHANGE"] = "1"
     torch.cuda.set_device(rank)
@@ -507,16 +514,18 @@ def _dist_worker(rank, world, port, q, dense):
         from smudgeplot_b200 import dist as hd
         job = hd.ShardedScan.from_synthetic(31, 500000, 3, 0.01, 60, 12, 4, torch.device("cuda", rank))
         plots = [job.scan().clone().cpu().numpy() for _ in range(3)]       # repeated: double buffering
+        assert job.symm_ok()
         q.put((rank, job.exchange, plots, job.n_total))
     finally:
         dist.barrier()
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("dense", [False, True])
-def test_one_process_per_gpu_nccl_matches_single_gpu(dense):
-    """torch.distributed/NCCL route (bench.py --gpus N): peer-mapped incidence arrays over CUDA IPC,
-    and the dense all-reduce fallback, against a single-GPU scan of the same seeded table"""
+@pytest.mark.parametrize("dense,path", [(False, "direct"), (True, "direct"), (False, "symm")])
+def test_one_process_per_gpu_nccl_matches_single_gpu(dense, path):
+    """torch.distributed/NCCL route (bench.py --gpus N): the sharded symmetric scan (Bloom segments
+    all-gathered), the direct passes over peer-mapped incidence arrays (CUDA IPC) and their dense
+    all-reduce fallback, against a single-GPU scan of the same seeded table"""
     import torch
     import torch.multiprocessing as mp
     from smudgeplot_b200.device import DeviceTable
@@ -525,8 +534,8 @@ def test_one_process_per_gpu_nccl_matches_single_gpu(dense):
         pytest.skip("needs 2 GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + (os.getpid() % 1000) + int(dense)
-    procs = [ctx.Process(target=_dist_worker, args=(r, world, port, q, dense)) for r in range(world)]
+    port = 29700 + (os.getpid() % 1000) + int(dense) + 2 * int(path == "symm")
+    procs = [ctx.Process(target=_dist_worker, args=(r, world, port, q, dense, path)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(world)]
@@ -534,10 +543,13 @@ def test_one_process_per_gpu_nccl_matches_single_gpu(dense):
         p.join(timeout=120)
         assert p.exitcode == 0
     keys, cnt = synth.synth_table(31, 500000, 3, 0.01, 60, 12, 4, device="cuda")
-    want = DeviceTable(31, keys, cnt.to(torch.int16)).build_index().scan().cpu().numpy().reshape(-1)
+    want = DeviceTable(31, keys, cnt.to(torch.int16)).build_index().scan("direct").cpu().numpy().reshape(-1)
     for rank, exchange, plots, n_total in res:
         assert n_total == keys.numel()
-        assert ("NCCL" in exchange) == dense, exchange
+        if path == "symm":
+            assert "Bloom" in exchange, exchange
+        else:
+            assert ("all-reduce" in exchange) == dense, exchange
         for p in plots:
             assert np.array_equal(p.reshape(-1), want)
 
