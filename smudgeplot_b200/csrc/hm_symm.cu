@@ -67,16 +67,27 @@ struct SymmView
     unsigned long long cand_cap;
   };
 
-/* Bloom slot of key (hi,lo): two bits of one 32-bit word of the owner's segment (one load per query) */
+/* Bloom slot of key (hi,lo).  The WORD is chosen by the key's last k/2 bases, the two BITS inside it by
+ * the bases before them: rc x and rc y of a candidate pair differ at one base of the front part only, so
+ * both of pass 2's look-ups for a pair fall into the same word -- one load (when one shard owns both). */
 template <int KW>
-__device__ __forceinline__ void bloom_slot(const SymmView &W, int seg, uint64_t hi, uint64_t lo,
+__device__ __forceinline__ void bloom_slot(const SymmView &W, int seg, int kmer, uint64_t hi, uint64_t lo,
                                            uint32_t *&word, uint32_t &mask)
-{ uint64_t v = hi;
-  if (KW == 2) v ^= lo * 0xD6E8FEB86659FD93ull;
-  uint64_t m = v * 0x9E3779B97F4A7C15ull;
-  uint32_t h = (uint32_t) (m >> 32);
+{ const int Pr = kmer >> 1, pup = kmer-Pr;
+  uint64_t sfx;                                                /* the last Pr bases, right aligned */
+  if (KW == 1)
+    sfx = hi >> (64-2*kmer);
+  else
+    { const int sr = 128-2*kmer;                               /* 0..62 */
+      sfx = sr == 0 ? lo : ((lo >> sr) | (hi << (64-sr)));
+    }
+  if (2*Pr < 64)
+    sfx &= (((uint64_t) 1 << (2*Pr)) - 1);
+  const uint64_t pfx = hi >> (64-2*pup);                       /* the first pup <= 32 bases */
+  const uint32_t h = (uint32_t) ((sfx * 0x9E3779B97F4A7C15ull) >> 32);
+  const uint32_t g = (uint32_t) ((pfx * 0xD6E8FEB86659FD93ull) >> 32);
   word = W.bloom + (size_t) seg * W.seg_words + __umulhi(h,W.seg_words);
-  mask = (1u << ((uint32_t) (m >> 27) & 31)) | (1u << ((uint32_t) (m >> 22) & 31));
+  mask = (1u << (g >> 27)) | (1u << ((g >> 22) & 31));
 }
 
 /* L2 residency: the Bloom segments (tens of MB) are what pass 2 hits at random, the candidate records
@@ -259,13 +270,39 @@ static SymmView make_view(void *d_work, const hm_symm_layout *L, const hm_symm_s
 
 /* shared-memory views of one CTA's window + its staging areas */
 template <int KW> struct RsSmem
-  { uint64_t *key, *klo;                /* window: RS_WIN slots                                   */
+  { uint64_t *key, *klo;                /* window: RS_WIN slots (+1 spare)                        */
     uint16_t *cnt;
     uint64_t *ckey, *clo, *cmeta;       /* staged candidate records: RS_STAGE                     */
-    uint16_t *t1, *t2;                  /* task lists: heads of 2-entry runs / members of longer runs */
+    uint16_t *t1;                       /* per warp: heads of two-entry runs (RS_TILE/2 in all)    */
+    uint16_t *t2r, *t2m;                /* CTA: first member of a longer run / members of very long runs */
   };
 
-/* stage one candidate record (warp-wide call; `emit` per lane) */
+__device__ __forceinline__ uint64_t pack_meta(int cx, int cy, int pos, int yb)
+{ return (uint64_t) cx | ((uint64_t) cy << 16) | ((uint64_t) pos << 32) | ((uint64_t) yb << 40); }
+
+/* one candidate record into the CTA's staging area (any lane, no collective) */
+template <int KW>
+__device__ __forceinline__ void stage_one(const RsSmem<KW> &S, unsigned *s_nc, const SymmView &W,
+                                          uint64_t x, uint64_t xl, uint64_t meta)
+{ unsigned at = atomicAdd(s_nc,1u);
+  if (at < RS_STAGE)
+    { S.ckey[at] = x;
+      if (KW == 2) S.clo[at] = xl;
+      S.cmeta[at] = meta;
+    }
+  else                                               /* staging full (dense tables): straight to the list */
+    { unsigned long long g1 = atomicAdd(W.cand_n,1ull);
+      if (g1 < W.cand_cap)
+        { W.cand_key[g1] = x;
+          if (KW == 2) W.cand_lo[g1] = xl;
+          W.cand_meta[g1] = meta;
+        }
+      else
+        atomicOr(W.status,SY_STATUS_OVERFLOW);
+    }
+}
+
+/* warp-wide variant: one shared atomic for all the lanes that emit */
 template <int KW>
 __device__ __forceinline__ void stage_candidates(const RsSmem<KW> &S, unsigned *s_nc, const SymmView &W,
                                                  bool emit, uint64_t x, uint64_t xl, uint64_t meta,
@@ -285,7 +322,7 @@ __device__ __forceinline__ void stage_candidates(const RsSmem<KW> &S, unsigned *
       if (KW == 2) S.clo[at] = xl;
       S.cmeta[at] = meta;
     }
-  else                                               /* staging full (dense tables): straight to the list */
+  else
     { unsigned long long g1 = atomicAdd(W.cand_n,1ull);
       if (g1 < W.cand_cap)
         { W.cand_key[g1] = x;
@@ -297,14 +334,69 @@ __device__ __forceinline__ void stage_candidates(const RsSmem<KW> &S, unsigned *
     }
 }
 
-/* any member of a run of three or more: scan the run both ways (H, U, partner) and, for the lower
+template <int KW>
+__device__ __forceinline__ void bloom_insert(const SymmView &W, int kmer, uint64_t x, uint64_t xl)
+{ uint32_t *word, mask;
+  bloom_slot<KW>(W,W.self,kmer,x,xl,word,mask);
+  atomicOr(word,mask);
+}
+
+/* A run of 3..8 entries, all of it inside the window: every pair once, partner counts of the members
+ * packed into nibbles.  `w` = the run's first member inside [a0,a1) (the slots this CTA answers for);
+ * members outside that range are only partners.  -> false if the run is longer (members go one by one) */
+template <int KW>
+__device__ __forceinline__ bool short_run(const RsSmem<KW> &S, unsigned *s_nc, const SymmView &W, int w,
+                                          int a0, int a1, uint64_t pmask, int kmer, int &b0, int &b1)
+{ const int pup = kmer - (kmer >> 1);
+  const uint64_t x0 = S.key[w];
+  b0 = w;
+  while (b0 > w-8 && ((S.key[b0-1] ^ x0) & pmask) == 0) b0 -= 1;
+  b1 = w+1;
+  while (b1 < b0+9 && ((S.key[b1] ^ x0) & pmask) == 0) b1 += 1;
+  const int L = b1-b0;
+  if (L > 8 || (b0 == w-8 && ((S.key[b0-1] ^ x0) & pmask) == 0))
+    return false;
+  uint32_t H = 0, U = 0, PT = 0;                       /* per member: partners, upper partners, last partner */
+  uint64_t PP = 0;                                     /* position of that partner's difference (8 bits each) */
+  for (int i = 0; i+1 < L; i++)
+    { const uint64_t xi = S.key[b0+i], xil = KW == 2 ? S.klo[b0+i] : 0;
+      const int      ci = S.cnt[b0+i];
+      for (int j = i+1; j < L; j++)
+        { int pos;
+          if (one_base_apart<KW>(xi,xil,S.key[b0+j],KW == 2 ? S.klo[b0+j] : 0,pos) &&
+              ci + (int) S.cnt[b0+j] <= HM_SMAX)
+            { H += (1u << (4*i)) + (1u << (4*j));
+              if (pos >= pup) U += (1u << (4*i)) + (1u << (4*j));
+              PT = (PT & ~((7u << (3*i)) | (7u << (3*j)))) | ((uint32_t) j << (3*i)) | ((uint32_t) i << (3*j));
+              PP = (PP & ~(((uint64_t) 255 << (8*i)) | ((uint64_t) 255 << (8*j)))) |
+                   ((uint64_t) pos << (8*i)) | ((uint64_t) pos << (8*j));
+            }
+        }
+    }
+  for (int i = 0; i < L; i++)
+    { const int slot = b0+i;
+      if (slot < a0 || slot >= a1) continue;
+      if (((U >> (4*i)) & 15) != 0)
+        bloom_insert<KW>(W,kmer,S.key[slot],KW == 2 ? S.klo[slot] : 0);
+      const int j = (int) ((PT >> (3*i)) & 7);
+      if (((H >> (4*i)) & 15) == 1 && j > i && ((H >> (4*j)) & 15) == 1)
+        { const int      pos = (int) ((PP >> (8*i)) & 255);
+          const uint64_t y = S.key[b0+j], yl = KW == 2 ? S.klo[b0+j] : 0;
+          stage_one<KW>(S,s_nc,W,S.key[slot],KW == 2 ? S.klo[slot] : 0,
+                        pack_meta(S.cnt[slot],S.cnt[b0+j],pos,base_at<KW>(y,yl,pos)));
+        }
+    }
+  return true;
+}
+
+/* any member of a run too long for short_run: scan the run both ways (H, U, partner) and, for the lower
  * member of a pair, the partner's H.  -> insert into the Bloom filter?  candidate record?          */
 template <typename IdxT, int KW>
-__device__ __forceinline__ void member_of_long_run(const RsSmem<KW> &S, int w, int v0, int v1, int64_t e0, int64_t e1,
-                                                   int64_t n, int64_t g, int kmer,
-                                                   const uint64_t *__restrict__ keys, const uint64_t *__restrict__ keys_lo,
-                                                   const uint16_t *__restrict__ cnt, const IdxT *__restrict__ bucket,
-                                                   int bshift, bool &insert, bool &emit, uint64_t &meta)
+__device__ __noinline__ void member_of_long_run(const RsSmem<KW> &S, int w, int v0, int v1, int64_t e0, int64_t e1,
+                                                int64_t n, int64_t g, int kmer,
+                                                const uint64_t *__restrict__ keys, const uint64_t *__restrict__ keys_lo,
+                                                const uint16_t *__restrict__ cnt, const IdxT *__restrict__ bucket,
+                                                int bshift, bool &insert, bool &emit, uint64_t &meta)
 { const int Pr = kmer >> 1, pup = kmer-Pr, psh = 64-2*Pr;
   const uint64_t x = S.key[w], xl = KW == 2 ? S.klo[w] : 0;
   const int cx = S.cnt[w];
@@ -348,8 +440,7 @@ __device__ __forceinline__ void member_of_long_run(const RsSmem<KW> &S, int w, i
             }
           if (Hy == 1)
             { emit = true;
-              meta = (uint64_t) cx | ((uint64_t) cy << 16) | ((uint64_t) ppos << 32) |
-                     ((uint64_t) base_at<KW>(y,yl,ppos) << 40);
+              meta = pack_meta(cx,cy,ppos,base_at<KW>(y,yl,ppos));
             }
         }
     }
@@ -364,8 +455,7 @@ __device__ __forceinline__ void member_of_long_run(const RsSmem<KW> &S, int w, i
           neighbours_slow<IdxT,KW>(keys,keys_lo,cnt,bucket,bshift,kmer,Pr,pup,y,yl,cy,Hy,Uy,party,py);
           if (Hy == 1)
             { emit = true;
-              meta = (uint64_t) cx | ((uint64_t) cy << 16) | ((uint64_t) ppos << 32) |
-                     ((uint64_t) base_at<KW>(y,yl,ppos) << 40);
+              meta = pack_meta(cx,cy,ppos,base_at<KW>(y,yl,ppos));
             }
         }
     }
@@ -373,10 +463,16 @@ __device__ __forceinline__ void member_of_long_run(const RsSmem<KW> &S, int w, i
 
 /* Pass 1.  83 % of the entries of a genome-sized table are alone in their run (no other entry shares
  * their first k/2 bases) and 15 % sit in a run of exactly two -- almost always the two alleles of one
- * heterozygous site.  So every entry is first only CLASSIFIED against its two neighbours on either
- * side (uniform, loop-free); heads of two-entry runs and members of longer runs are compacted into
- * two task lists in shared memory and worked off with every lane busy.  (Scanning every entry's run
- * in place cost 436 warp instructions per 32 entries at 34 % lane utilisation.)                     */
+ * heterozygous site.  The kernel is bound by instruction issue, not by bytes (55 warp instructions per
+ * 32 entries is all a B200 can issue while HBM delivers them), so the common cases are kept loop-free:
+ *   1. adjacency bits: eq[i] = slots i, i+1 belong to one run             (one ballot per 32 slots)
+ *   2. classification of 8 x 32 entries per warp with bit operations, one WORD PER LANE:
+ *      head of a two-entry run / first member of a longer run / nothing
+ *   3. two-entry runs: one comparison settles both members (per-warp task list, every lane busy)
+ *   4. longer runs: one thread per run, all pairs once (short_run); members of runs of more than 8
+ *      one by one (member_of_long_run)
+ * (Scanning every entry's run in place cost 436 warp instructions per 32 entries at 34 % lane
+ * utilisation; per-entry classification with predicated list writes still 163.)                   */
 template <typename IdxT, int KW>
 __global__ void __launch_bounds__(RS_THREADS)
 runscan_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ keys_lo,
@@ -384,24 +480,27 @@ runscan_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ k
                int kmer, int64_t lo, int64_t hi, int64_t tile0, int use_tma, const SymmView W)
 { extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t s_bar;
-  __shared__ unsigned s_nc, s_n1, s_n2;
+  __shared__ unsigned s_nc, s_n2r, s_n2m;
   __shared__ unsigned s_eq[RS_WIN/32];
   __shared__ unsigned long long s_base;
   RsSmem<KW> S;
-  S.key   = (uint64_t *) smem;
-  S.klo   = S.key + (KW == 2 ? RS_WIN : 0);
-  S.ckey  = S.key + KW*RS_WIN;
+  S.key   = (uint64_t *) smem;                               /* RS_WIN+2 slots each (spare: sentinel) */
+  S.klo   = S.key + (KW == 2 ? RS_WIN+2 : 0);
+  S.ckey  = S.key + KW*(RS_WIN+2);
   S.clo   = S.ckey + (KW == 2 ? RS_STAGE : 0);
   S.cmeta = S.ckey + KW*RS_STAGE;
   S.cnt   = (uint16_t *) (S.cmeta + RS_STAGE);
-  S.t1    = S.cnt + RS_WIN;
-  S.t2    = S.t1 + RS_TILE/2;
+  S.t1    = S.cnt + RS_WIN+8;
+  S.t2r   = S.t1 + RS_TILE/2;
+  S.t2m   = S.t2r + RS_TILE/2;
 
   const int      Pr   = kmer >> 1;                 /* run = entries sharing their first Pr bases     */
   const int      pup  = kmer - Pr;                 /* positions >= pup have a mirror position < Pr   */
   const int      psh  = 64-2*Pr;
+  const uint64_t pmask = ~(uint64_t) 0 << psh;
   const unsigned FULL = 0xffffffffu;
   const int      lane = threadIdx.x & 31;
+  const int      warp = threadIdx.x >> 5;
   const unsigned lt   = (1u << lane) - 1;
 
   const int64_t T0 = (tile0 + blockIdx.x) * RS_TILE;
@@ -414,7 +513,7 @@ runscan_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ k
   const int m   = v1-v0;
   const int mt  = use_tma ? (m & ~7) : 0;
   if (threadIdx.x == 0)
-    { s_nc = 0; s_n1 = 0; s_n2 = 0;
+    { s_nc = 0; s_n2r = 0; s_n2m = 0;
       if (mt > 0)
         { mbar_init(&s_bar,1);
           fence_proxy_async_smem();
@@ -433,17 +532,30 @@ runscan_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ k
       if (KW == 2) S.klo[v0+j] = keys_lo[e0+j];
       S.cnt[v0+j] = cnt[e0+j];
     }
-  __syncthreads();
   if (mt > 0)
     mbar_wait(&s_bar,0);
+  __syncthreads();
+  /* slots outside the table (first / last tile): a key no neighbour can share a run with */
+  if (v0 > 0 || v1 < RS_WIN)
+    { const uint64_t sa = ~S.key[v0], sb = ~S.key[v1-1];
+      __syncthreads();
+      for (int j = threadIdx.x; j < RS_WIN; j += RS_THREADS)
+        if (j < v0)       S.key[j] = sa;
+        else if (j >= v1) S.key[j] = sb;
+      __syncthreads();
+    }
 
-  /* ---- adjacency bits: eq[i] = slots i and i+1 hold entries of one run (bit i%32 of word i/32) ---- */
-  const uint64_t pmask = ~(uint64_t) 0 << psh;                    /* the first Pr bases */
-  const int      warp  = threadIdx.x >> 5;
-  for (int wd = warp; wd < RS_WIN/32; wd += RS_THREADS/32)
-    { const int  i  = wd*32 + lane;
-      bool eq = false;
-      if (i >= v0 && i+1 < v1)
+  /* ---- 1. adjacency bits ---- */
+  for (int wd = 1+warp; wd < RS_WIN/32-1; wd += RS_THREADS/32)       /* (the outermost two words are never looked at) */
+    { const int i = wd*32 + lane;
+      bool eq;
+      if (psh >= 32)                                   /* k <= 33: the first Pr bases sit in the upper word */
+        { const uint32_t a = (uint32_t) (S.key[i] >> 32);
+          uint32_t       b = __shfl_down_sync(FULL,a,1);
+          if (lane == 31) b = (uint32_t) (S.key[i+1] >> 32);
+          eq = (((a ^ b) >> (psh-32)) == 0);
+        }
+      else
         eq = (((S.key[i] ^ S.key[i+1]) & pmask) == 0);
       const unsigned bal = __ballot_sync(FULL,eq);
       if (lane == 0)
@@ -451,51 +563,58 @@ runscan_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ k
     }
   __syncthreads();
 
-  /* ---- classify 32 entries at a time with bit operations (warp-uniform): head of a run of exactly two
-   *      (its tail stays silent) / member of a longer run / neither                                 ---- */
-  { const int tlo = lo > T0 ? (int) (lo-T0 < RS_TILE ? lo-T0 : RS_TILE) : 0;      /* tile slots of [lo,hi) */
-    const int thi = hi-T0 < RS_TILE ? (int) (hi-T0) : RS_TILE;
-    unsigned m2[RS_EPT], m3[RS_EPT];
-    int      c2 = 0, c3 = 0;
-#pragma unroll
-    for (int e = 0; e < RS_EPT; e++)
-      { const int      wd = RS_HALO/32 + warp*RS_EPT + e;             /* this warp's e-th word of the tile */
-        const unsigned E = s_eq[wd], P = s_eq[wd-1], N = s_eq[wd+1];
+  /* ---- 2. classify: lane e < RS_EPT takes the e-th of this warp's words of the tile ---- */
+  const int a0 = RS_HALO + (lo > T0 ? (int) (lo-T0 < RS_TILE ? lo-T0 : RS_TILE) : 0);   /* slots this CTA answers for */
+  const int a1 = RS_HALO + (hi-T0 < RS_TILE ? (int) (hi-T0) : RS_TILE);
+  uint16_t *my1 = S.t1 + warp*(RS_TILE/2/(RS_THREADS/32));
+  int n1;
+  { unsigned m2 = 0, m3 = 0;
+    const int wd = RS_HALO/32 + warp*RS_EPT + lane;
+    if (lane < RS_EPT)
+      { const unsigned E = s_eq[wd], P = s_eq[wd-1], N = s_eq[wd+1];
         const unsigned em1 = (E << 1) | (P >> 31);                     /* eq[w-1] */
         const unsigned em2 = (E << 2) | (P >> 30);                     /* eq[w-2] */
         const unsigned ep1 = (E >> 1) | (N << 31);                     /* eq[w+1] */
-        const int      t0  = (wd - RS_HALO/32)*32;                     /* tile slot of bit 0 */
-        unsigned act = 0xffffffffu;
-        if (t0 < tlo)      act &= (tlo-t0 >= 32) ? 0u : (0xffffffffu << (tlo-t0));
-        if (t0+32 > thi)   act &= (thi-t0 <= 0)  ? 0u : (0xffffffffu >> (t0+32-thi));
-        m3[e] = ((em1 & E) | (E & ep1) | (em1 & em2)) & act;
-        m2[e] = (E & ~em1 & ~ep1) & act;
-        c2 += __popc(m2[e]); c3 += __popc(m3[e]);
+        const int      s0  = wd*32;                                    /* slot of bit 0 */
+        unsigned act = 0xffffffffu, actp;                              /* actp: is slot-1 answered for, too? */
+        if (s0 < a0)      act &= (a0-s0 >= 32) ? 0u : (0xffffffffu << (a0-s0));
+        if (s0+32 > a1)   act &= (a1-s0 <= 0)  ? 0u : (0xffffffffu >> (s0+32-a1));
+        actp = (act << 1) | ((s0-1 >= a0 && s0-1 < a1) ? 1u : 0u);
+        const unsigned more = (em1 & E) | (E & ep1) | (em1 & em2);
+        m2 = (E & ~em1 & ~ep1) & act;                                  /* head of a run of exactly two */
+        m3 = more & act & ~(em1 & actp);                               /* first answered-for member of a longer run */
       }
-    unsigned b2 = 0, b3 = 0;
-    if (lane == 0)
-      { if (c2 > 0) b2 = atomicAdd(&s_n1,(unsigned) c2);
-        if (c3 > 0) b3 = atomicAdd(&s_n2,(unsigned) c3);
-      }
-    b2 = __shfl_sync(FULL,b2,0); b3 = __shfl_sync(FULL,b3,0);
+    /* per-warp list of the two-run heads: exclusive scan of the counts over the RS_EPT lanes */
+    const int c2 = __popc(m2);
+    int pre = c2;
 #pragma unroll
-    for (int e = 0; e < RS_EPT; e++)
-      { const int w = (RS_HALO/32 + warp*RS_EPT + e)*32 + lane;
-        if ((m2[e] >> lane) & 1) S.t1[b2 + __popc(m2[e] & lt)] = (uint16_t) w;
-        if ((m3[e] >> lane) & 1) S.t2[b3 + __popc(m3[e] & lt)] = (uint16_t) w;
-        b2 += __popc(m2[e]); b3 += __popc(m3[e]);
+    for (int o = 1; o < RS_EPT; o <<= 1)
+      { int v = __shfl_up_sync(FULL,pre,o);
+        if (lane >= o) pre += v;
+      }
+    n1 = __shfl_sync(FULL,pre,RS_EPT-1);
+    int at = pre-c2;
+    while (m2 != 0)
+      { my1[at++] = (uint16_t) (wd*32 + __ffs(m2)-1);
+        m2 &= m2-1;
+      }
+    if (m3 != 0)
+      { unsigned at3 = atomicAdd(&s_n2r,(unsigned) __popc(m3));
+        while (m3 != 0)
+          { S.t2r[at3++] = (uint16_t) (wd*32 + __ffs(m3)-1);
+            m3 &= m3-1;
+          }
       }
   }
-  __syncthreads();
+  __syncwarp();
 
-  /* ---- runs of two: one comparison settles both members ---- */
-  const int n1 = (int) s_n1, n2 = (int) s_n2;
-  for (int i0 = (threadIdx.x & ~31); i0 < n1; i0 += RS_THREADS)
+  /* ---- 3. runs of two: one comparison settles both members ---- */
+  for (int i0 = 0; i0 < n1; i0 += 32)
     { const int i = i0+lane;
       bool     emit = false;
       uint64_t x = 0, xl = 0, meta = 0;
       if (i < n1)
-        { const int w = S.t1[i];
+        { const int w = my1[i];
           x = S.key[w];
           const uint64_t y = S.key[w+1];
           uint64_t yl = 0;
@@ -504,43 +623,52 @@ runscan_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ k
           int pos;
           if (one_base_apart<KW>(x,xl,y,yl,pos) && cx+cy <= HM_SMAX)      /* H(x) = H(y) = 1 */
             { emit = true;
-              meta = (uint64_t) cx | ((uint64_t) cy << 16) | ((uint64_t) pos << 32) |
-                     ((uint64_t) base_at<KW>(y,yl,pos) << 40);
+              meta = pack_meta(cx,cy,pos,base_at<KW>(y,yl,pos));
               if (pos >= pup)                                              /* U(x) = U(y) = 1: both are in S */
-                { uint32_t *word, mask;
-                  bloom_slot<KW>(W,W.self,x,xl,word,mask);
-                  atomicOr(word,mask);
-                  bloom_slot<KW>(W,W.self,y,yl,word,mask);
-                  atomicOr(word,mask);
+                { bloom_insert<KW>(W,kmer,x,xl);
+                  bloom_insert<KW>(W,kmer,y,yl);
                 }
             }
         }
       stage_candidates<KW>(S,&s_nc,W,emit,x,xl,meta,lane,lt);
     }
+  __syncthreads();
 
-  /* ---- longer runs: every member on its own ---- */
-  for (int i0 = (threadIdx.x & ~31); i0 < n2; i0 += RS_THREADS)
-    { const int i = i0+lane;
-      bool     emit = false, insert = false;
-      uint64_t x = 0, xl = 0, meta = 0;
-      if (i < n2)
-        { const int w = S.t2[i];
-          x = S.key[w];
-          if (KW == 2) xl = S.klo[w];
-          member_of_long_run<IdxT,KW>(S,w,v0,v1,e0,e1,n,T0+(w-RS_HALO),kmer,keys,keys_lo,cnt,bucket,bshift,
-                                      insert,emit,meta);
+  /* ---- 4. longer runs: one thread per run; members of runs of more than 8 go to the second list ---- */
+  const int n2r = (int) s_n2r;
+  for (int i = threadIdx.x; i < n2r; i += RS_THREADS)
+    { const int w = S.t2r[i];
+      int b0, b1;
+      if (!short_run<KW>(S,&s_nc,W,w,a0,a1,pmask,kmer,b0,b1))
+        { /* hand every answered-for member from w to the end of the run (or of the tile) to the list */
+          const uint64_t x0 = S.key[w];
+          for (int j = w; j < a1 && ((S.key[j] ^ x0) & pmask) == 0; j++)
+            S.t2m[atomicAdd(&s_n2m,1u)] = (uint16_t) j;
         }
-      if (insert)
-        { uint32_t *word, mask;
-          bloom_slot<KW>(W,W.self,x,xl,word,mask);
-          atomicOr(word,mask);
+    }
+  __syncthreads();
+  const int n2m = (int) s_n2m;
+  if (n2m > 0)
+    { for (int i0 = (threadIdx.x & ~31); i0 < n2m; i0 += RS_THREADS)
+        { const int i = i0+lane;
+          bool     emit = false, insert = false;
+          uint64_t x = 0, xl = 0, meta = 0;
+          if (i < n2m)
+            { const int w = S.t2m[i];
+              x = S.key[w];
+              if (KW == 2) xl = S.klo[w];
+              member_of_long_run<IdxT,KW>(S,w,v0,v1,e0,e1,n,T0+(w-RS_HALO),kmer,keys,keys_lo,cnt,bucket,bshift,
+                                          insert,emit,meta);
+            }
+          if (insert)
+            bloom_insert<KW>(W,kmer,x,xl);
+          stage_candidates<KW>(S,&s_nc,W,emit,x,xl,meta,lane,lt);
         }
-      stage_candidates<KW>(S,&s_nc,W,emit,x,xl,meta,lane,lt);
+      __syncthreads();
     }
 
   /* ---- the staged records leave the CTA in one piece: one global atomic per CTA (one per record, or
    *      per warp, on the one list counter serialises in L2: 9.2 ms for 1.8e7 records)            ---- */
-  __syncthreads();
   const unsigned nc = s_nc < RS_STAGE ? s_nc : RS_STAGE;
   if (nc == 0)
     return;
@@ -564,7 +692,8 @@ static cudaError_t launch_runscan(const uint64_t *keys, const uint64_t *keys_lo,
                                   const void *bucket, int bits, int kmer, int64_t lo, int64_t hi,
                                   const SymmView &W, cudaStream_t st)
 { static int configured[64] = {0};                            /* per instantiation */
-  size_t smem = (size_t) RS_WIN*(8*KW+2) + (size_t) RS_STAGE*8*(KW+1) + 2*(RS_TILE/2+RS_TILE);   /* 40 KB (k <= 32) / 64 KB */
+  size_t smem = (size_t) (RS_WIN+2)*8*KW + (size_t) (RS_WIN+8)*2 + (size_t) RS_STAGE*8*(KW+1) +
+                2*(size_t) (RS_TILE/2+RS_TILE/2+RS_TILE);                            /* 38 KB (k <= 32) / 59 KB */
   int dev = 0;
   cudaGetDevice(&dev);
   if (smem > 48*1024 && (dev >= 64 || !configured[dev]))
@@ -620,19 +749,41 @@ extern "C" int hm_k_symm_runscan(const uint64_t *d_keys, const uint64_t *d_keys_
 #define RV_THREADS 512
 #define RV_CTAS_PER_SM 3
 
-/* does table entry q have a partner at a position >= pup?  (exact; q must be in the table) */
+/* does table entry q (count cq: the table is symmetric, so it is the count of the candidate member
+ * whose reverse complement q is) have a partner at a position >= pup?  Exact.  The bucket index is at
+ * most as fine as a run (bits <= 2*Pr), so q's bucket holds q's whole run: one pass over those few keys
+ * finds q itself and its partners -- bucket offsets -> keys -> counts, three dependent accesses.        */
 template <typename IdxT, int KW>
 __device__ __noinline__ bool has_upper_partner(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ keys_lo,
                                                const uint16_t *__restrict__ cnt, int64_t n,
                                                const IdxT *__restrict__ bucket, int bshift, int kmer,
-                                               uint64_t q, uint64_t ql, unsigned long long *status)
+                                               uint64_t q, uint64_t ql, int cq, unsigned long long *status)
 { const int Pr = kmer >> 1, pup = kmer-Pr, psh = 64-2*Pr;
+  if (bshift >= psh)                                            /* bucket prefix no longer than the run prefix */
+    { const uint64_t bk = q >> bshift;
+      const int64_t  l = (int64_t) bucket[bk], r = (int64_t) bucket[bk+1];
+      if (r-l <= 48)
+        { bool found = false, hit = false;
+          for (int64_t i = l; i < r; i++)
+            { const uint64_t z = __ldg(keys+i), zl = KW == 2 ? __ldg(keys_lo+i) : 0;
+              if (z == q && (KW == 1 || zl == ql))
+                { found = true; continue; }
+              if (((z ^ q) >> psh) != 0)
+                continue;
+              int pos;
+              if (one_base_apart<KW>(q,ql,z,zl,pos) && pos >= pup && cq + (int) __ldg(cnt+i) <= HM_SMAX)
+                hit = true;
+            }
+          if (!found)
+            atomicOr(status,SY_STATUS_ASYMMETRIC);
+          return hit;
+        }
+    }
   int64_t j = bucket_find<IdxT,KW>(keys,keys_lo,bucket,bshift,q,ql);
   if (j < 0)
     { atomicOr(status,SY_STATUS_ASYMMETRIC);
       return true;
     }
-  const int cq = __ldg(cnt+j);
   bool capped = false;
   for (int dir = -1; dir <= 1; dir += 2)
     { int steps = 0;
@@ -653,29 +804,32 @@ __device__ __noinline__ bool has_upper_partner(const uint64_t *__restrict__ keys
   return (U > 0);
 }
 
-/* one candidate: are rc x / rc y in S?  Bloom bits first; `exact` = also settle the hits.
- * -> 0 isolated pair, 1 not isolated, 2 undecided (a Bloom hit, exact == false)                  */
+/* one candidate: are rc x / rc y in S?  Bloom bits first; EXACT = also settle the hits.
+ * -> 0 isolated pair, 1 not isolated, 2 undecided (a Bloom hit, EXACT == false)                  */
 template <typename IdxT, int KW, bool EXACT>
 __device__ __forceinline__ int judge_candidate(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ keys_lo,
                                                const uint16_t *__restrict__ cnt, int64_t n,
                                                const IdxT *__restrict__ bucket, int bshift, int kmer,
                                                const SymmView &W, uint64_t x, uint64_t xl, uint64_t meta)
-{ const int p  = (int) ((meta >> 32) & 0xff), yb = (int) ((meta >> 40) & 3);
+{ const int cx = (int) (meta & 0xffff), cy = (int) ((meta >> 16) & 0xffff);
+  const int p  = (int) ((meta >> 32) & 0xff), yb = (int) ((meta >> 40) & 3);
   uint64_t rx, rxl, ry, ryl;
   revcomp_kmer<KW>(x,xl,kmer,rx,rxl);
   ry = rx; ryl = rxl;
   set_base<KW>(ry,ryl,kmer-1-p,3-yb);                      /* rc y = rc x with the mirrored base swapped */
   uint32_t *wa, *wb, ba, bb;
-  bloom_slot<KW>(W,W.n_seg > 1 ? owner_of(W,rx) : 0,rx,rxl,wa,ba);
-  bloom_slot<KW>(W,W.n_seg > 1 ? owner_of(W,ry) : 0,ry,ryl,wb,bb);
-  const bool ha = (ld_keep(wa) & ba) == ba, hb = (ld_keep(wb) & bb) == bb;
+  bloom_slot<KW>(W,W.n_seg > 1 ? owner_of(W,rx) : 0,kmer,rx,rxl,wa,ba);
+  bloom_slot<KW>(W,W.n_seg > 1 ? owner_of(W,ry) : 0,kmer,ry,ryl,wb,bb);
+  const uint32_t va = ld_keep(wa);
+  const uint32_t vb = (wb == wa) ? va : ld_keep(wb);       /* one shard owns both: the same word */
+  const bool ha = (va & ba) == ba, hb = (vb & bb) == bb;
   if (!ha && !hb)
     return 0;
   if (!EXACT)
     return 2;
-  if (ha && has_upper_partner<IdxT,KW>(keys,keys_lo,cnt,n,bucket,bshift,kmer,rx,rxl,W.status))
+  if (ha && has_upper_partner<IdxT,KW>(keys,keys_lo,cnt,n,bucket,bshift,kmer,rx,rxl,cx,W.status))
     return 1;
-  if (hb && has_upper_partner<IdxT,KW>(keys,keys_lo,cnt,n,bucket,bshift,kmer,ry,ryl,W.status))
+  if (hb && has_upper_partner<IdxT,KW>(keys,keys_lo,cnt,n,bucket,bshift,kmer,ry,ryl,cy,W.status))
     return 1;
   return 0;
 }
