@@ -156,12 +156,13 @@ int hm_k_pass2_extract(const uint64_t *d_keys, const uint64_t *d_keys_lo, const 
 
 typedef struct hm_symm_layout               /* work area of one scan range (hm_symm_plan fills it in)     */
   { int64_t bytes;                          /* device bytes to allocate (256-byte aligned)                */
-    int64_t off_header;                     /* uint64[2]: candidate count, status bits (hm_symm_status)   */
+    int64_t off_header;                     /* uint64[3]: candidate count, status bits (hm_symm_status), runs */
     int64_t off_bloom;                      /* n_seg segments of seg_words uint32: Bloom filter over the  */
     int64_t seg_words;                      /*   entries with a partner in their upper half, per shard    */
     int64_t off_cand_key, off_cand_lo, off_cand_meta;   /* candidate pair records                         */
     int64_t cand_cap;
     int64_t range;
+    int64_t off_runs, runs_cap;             /* heads of the runs of three or more entries (uint64 indices) */
     int32_t n_seg, pad;
   } hm_symm_layout;
 

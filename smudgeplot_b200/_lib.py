@@ -48,7 +48,8 @@ class SymmLayout(C.Structure):
     """hm_symm_layout: work area of the strand-symmetric scan"""
     _fields_ = [("bytes", C.c_int64), ("off_header", C.c_int64), ("off_bloom", C.c_int64), ("seg_words", C.c_int64),
                 ("off_cand_key", C.c_int64), ("off_cand_lo", C.c_int64), ("off_cand_meta", C.c_int64),
-                ("cand_cap", C.c_int64), ("range", C.c_int64), ("n_seg", C.c_int32), ("pad", C.c_int32)]
+                ("cand_cap", C.c_int64), ("range", C.c_int64), ("off_runs", C.c_int64), ("runs_cap", C.c_int64),
+                ("n_seg", C.c_int32), ("pad", C.c_int32)]
 
 
 class SymmShards(C.Structure):

@@ -50,6 +50,9 @@
 #define RS_HALO    64                          /* entries staged on either side of the tile      */
 #define RS_WIN     (RS_TILE+2*RS_HALO)
 #define RS_SCANCAP RS_HALO                     /* longest run half scanned linearly               */
+#ifndef RS_MINBLOCKS
+#define RS_MINBLOCKS 5                         /* resident CTAs per SM the register budget must allow          */
+#endif
 #define RS_STAGE   512                         /* candidate records staged per CTA before they leave */
 
 #define SY_STATUS_ASYMMETRIC 1ull              /* a reverse complement was not in the table      */
@@ -65,6 +68,9 @@ struct SymmView
     uint64_t  first_key[HM_MAX_SHARDS];         /* word 0 of the first key of segments 1.. (0 unused) */
     uint64_t *cand_key, *cand_lo, *cand_meta;
     unsigned long long cand_cap;
+    unsigned long long *runs_n;                 /* heads of runs of three or more entries (table indices) */
+    uint64_t *runs;
+    unsigned long long runs_cap;
   };
 
 /* Bloom slot of key (hi,lo).  The WORD is chosen by the key's last k/2 bases, the two BITS inside it by
@@ -239,6 +245,7 @@ extern "C" int hm_symm_plan(int64_t n, int64_t range, int kmer, int n_seg, hm_sy
   out->off_cand_lo = at;    at += (kmer > 32) ? 8*cap : 0;
   out->off_cand_meta = at;  at += 8*cap;
   out->cand_cap = cap;
+  out->off_runs = at;       out->runs_cap = range/3 + 1024;   at += 8*out->runs_cap;
   out->n_seg = n_seg;
   out->range = range;
   out->bytes = (at+255) & ~255ll;
@@ -263,6 +270,9 @@ static SymmView make_view(void *d_work, const hm_symm_layout *L, const hm_symm_s
   W.cand_lo   = (uint64_t *) (b + L->off_cand_lo);
   W.cand_meta = (uint64_t *) (b + L->off_cand_meta);
   W.cand_cap  = (unsigned long long) L->cand_cap;
+  W.runs_n    = W.cand_n + 2;
+  W.runs      = (uint64_t *) (b + L->off_runs);
+  W.runs_cap  = (unsigned long long) L->runs_cap;
   return W;
 }
 
@@ -274,7 +284,7 @@ template <int KW> struct RsSmem
     uint16_t *cnt;
     uint64_t *ckey, *clo, *cmeta;       /* staged candidate records: RS_STAGE                     */
     uint16_t *t1;                       /* per warp: heads of two-entry runs (RS_TILE/2 in all)    */
-    uint16_t *t2r, *t2m;                /* CTA: first member of a longer run / members of very long runs */
+    uint16_t *t2r;                      /* CTA: heads of longer runs                               */
   };
 
 __device__ __forceinline__ uint64_t pack_meta(int cx, int cy, int pos, int yb)
@@ -341,121 +351,158 @@ __device__ __forceinline__ void bloom_insert(const SymmView &W, int kmer, uint64
   atomicOr(word,mask);
 }
 
-/* A run of 3..8 entries, all of it inside the window: every pair once, partner counts of the members
- * packed into nibbles.  `w` = the run's first member inside [a0,a1) (the slots this CTA answers for);
- * members outside that range are only partners.  -> false if the run is longer (members go one by one) */
-template <int KW>
-__device__ __forceinline__ bool short_run(const RsSmem<KW> &S, unsigned *s_nc, const SymmView &W, int w,
-                                          int a0, int a1, uint64_t pmask, int kmer, int &b0, int &b1)
-{ const int pup = kmer - (kmer >> 1);
-  const uint64_t x0 = S.key[w];
-  b0 = w;
-  while (b0 > w-8 && ((S.key[b0-1] ^ x0) & pmask) == 0) b0 -= 1;
-  b1 = w+1;
-  while (b1 < b0+9 && ((S.key[b1] ^ x0) & pmask) == 0) b1 += 1;
-  const int L = b1-b0;
-  if (L > 8 || (b0 == w-8 && ((S.key[b0-1] ^ x0) & pmask) == 0))
-    return false;
-  uint32_t H = 0, U = 0, PT = 0;                       /* per member: partners, upper partners, last partner */
-  uint64_t PP = 0;                                     /* position of that partner's difference (8 bits each) */
-  for (int i = 0; i+1 < L; i++)
-    { const uint64_t xi = S.key[b0+i], xil = KW == 2 ? S.klo[b0+i] : 0;
-      const int      ci = S.cnt[b0+i];
-      for (int j = i+1; j < L; j++)
-        { int pos;
-          if (one_base_apart<KW>(xi,xil,S.key[b0+j],KW == 2 ? S.klo[b0+j] : 0,pos) &&
-              ci + (int) S.cnt[b0+j] <= HM_SMAX)
-            { H += (1u << (4*i)) + (1u << (4*j));
-              if (pos >= pup) U += (1u << (4*i)) + (1u << (4*j));
-              PT = (PT & ~((7u << (3*i)) | (7u << (3*j)))) | ((uint32_t) j << (3*i)) | ((uint32_t) i << (3*j));
-              PP = (PP & ~(((uint64_t) 255 << (8*i)) | ((uint64_t) 255 << (8*j)))) |
-                   ((uint64_t) pos << (8*i)) | ((uint64_t) pos << (8*j));
-            }
-        }
-    }
-  for (int i = 0; i < L; i++)
-    { const int slot = b0+i;
-      if (slot < a0 || slot >= a1) continue;
-      if (((U >> (4*i)) & 15) != 0)
-        bloom_insert<KW>(W,kmer,S.key[slot],KW == 2 ? S.klo[slot] : 0);
-      const int j = (int) ((PT >> (3*i)) & 7);
-      if (((H >> (4*i)) & 15) == 1 && j > i && ((H >> (4*j)) & 15) == 1)
-        { const int      pos = (int) ((PP >> (8*i)) & 255);
-          const uint64_t y = S.key[b0+j], yl = KW == 2 ? S.klo[b0+j] : 0;
-          stage_one<KW>(S,s_nc,W,S.key[slot],KW == 2 ? S.klo[slot] : 0,
-                        pack_meta(S.cnt[slot],S.cnt[b0+j],pos,base_at<KW>(y,yl,pos)));
-        }
-    }
-  return true;
-}
-
-/* any member of a run too long for short_run: scan the run both ways (H, U, partner) and, for the lower
- * member of a pair, the partner's H.  -> insert into the Bloom filter?  candidate record?          */
+/* Pass 1b: the runs of three or more entries (1-2 % of the entries; collisions of a heterozygous pair
+ * with an unrelated k-mer, repeats, low-complexity sequence) are irregular work: runscan_kernel only
+ * lists their heads, this kernel takes one run per thread, straight from global memory (the keys of a
+ * run are neighbours in the table).
+ *   3..8 entries: every pair once, the members' partner counts packed into nibbles
+ *   longer:       the warp takes the run together, one member per lane and trip, with one bucket
+ *                 look-up per candidate partner (neighbours_slow) -- dense / tiny-k tables live here   */
 template <typename IdxT, int KW>
-__device__ __noinline__ void member_of_long_run(const RsSmem<KW> &S, int w, int v0, int v1, int64_t e0, int64_t e1,
-                                                int64_t n, int64_t g, int kmer,
-                                                const uint64_t *__restrict__ keys, const uint64_t *__restrict__ keys_lo,
-                                                const uint16_t *__restrict__ cnt, const IdxT *__restrict__ bucket,
-                                                int bshift, bool &insert, bool &emit, uint64_t &meta)
-{ const int Pr = kmer >> 1, pup = kmer-Pr, psh = 64-2*Pr;
-  const uint64_t x = S.key[w], xl = KW == 2 ? S.klo[w] : 0;
-  const int cx = S.cnt[w];
-  int  H = 0, U = 0, pj = -1, ppos = 0;
-  bool ovf = false;
-  int  b0, b1, j;
-  insert = false; emit = false; meta = 0;
-  { int lim = w-RS_SCANCAP > v0 ? w-RS_SCANCAP : v0;               /* backward half of the run */
-    for (j = w-1; j >= lim; j--)
-      { uint64_t z = S.key[j];
-        if (((z ^ x) >> psh) != 0) break;
-        int pos;
-        if (one_base_apart<KW>(x,xl,z,KW == 2 ? S.klo[j] : 0,pos) && cx + (int) S.cnt[j] <= HM_SMAX)
-          { H += 1; U += (pos >= pup); pj = j; ppos = pos; }
-      }
-    if (j < lim && !(lim == v0 && e0 == 0)) ovf = true;             /* run longer than the window */
-    b0 = j+1;
-  }
-  { int lim = w+RS_SCANCAP < v1-1 ? w+RS_SCANCAP : v1-1;           /* forward half */
-    for (j = w+1; j <= lim; j++)
-      { uint64_t z = S.key[j];
-        if (((z ^ x) >> psh) != 0) break;
-        int pos;
-        if (one_base_apart<KW>(x,xl,z,KW == 2 ? S.klo[j] : 0,pos) && cx + (int) S.cnt[j] <= HM_SMAX)
-          { H += 1; U += (pos >= pup); pj = j; ppos = pos; }
-      }
-    if (j > lim && !(lim == v1-1 && e1 == n)) ovf = true;
-    b1 = j;
-  }
-  if (!ovf)
-    { insert = (U > 0);
-      if (H == 1 && pj > w)                            /* x is the lower member: is y's only partner x? */
-        { uint64_t y = S.key[pj], yl = KW == 2 ? S.klo[pj] : 0;
-          const int cy = S.cnt[pj];
-          int Hy = 0;
-          for (j = b0; j < b1 && Hy < 2; j++)
-            { if (j == pj) continue;
-              int pos;
-              if (one_base_apart<KW>(y,yl,S.key[j],KW == 2 ? S.klo[j] : 0,pos) && cy + (int) S.cnt[j] <= HM_SMAX)
-                Hy += 1;
+__global__ void __launch_bounds__(256)
+runs_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ keys_lo,
+            const uint16_t *__restrict__ cnt, int64_t n, const IdxT *__restrict__ bucket, int bshift,
+            int kmer, int64_t lo, int64_t hi, const SymmView W)
+{ const int      Pr = kmer >> 1, pup = kmer-Pr, psh = 64-2*Pr;
+  const uint64_t pmask = ~(uint64_t) 0 << psh;
+  const unsigned FULL = 0xffffffffu;
+  const int      lane = threadIdx.x & 31;
+  const unsigned lt   = (1u << lane) - 1;
+  unsigned long long nrl = *W.runs_n;
+  if (nrl > W.runs_cap) nrl = W.runs_cap;
+  const int64_t nr     = (int64_t) nrl;
+  const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t r0 = (int64_t) blockIdx.x * blockDim.x + threadIdx.x - lane; r0 < nr; r0 += stride)
+    { const int64_t r = r0+lane;
+      const bool    valid = (r < nr);
+      int64_t  h = 0;
+      uint64_t x0 = 0;
+      int      L = 1;
+      if (valid)
+        { h  = (int64_t) W.runs[r];
+          x0 = __ldg(keys+h);
+          while (L <= 8 && h+L < n && ((__ldg(keys+h+L) ^ x0) & pmask) == 0)
+            L += 1;
+        }
+      const bool islong = valid && (L > 8);
+      /* ---- short run: all pairs ---- */
+      uint32_t H = 0, U = 0, PT = 0;
+      uint64_t PP = 0;
+      int      nrec = 0;
+      if (valid && !islong)
+        { for (int i = 0; i+1 < L; i++)
+            { const uint64_t xi = __ldg(keys+h+i), xil = KW == 2 ? __ldg(keys_lo+h+i) : 0;
+              const int      ci = __ldg(cnt+h+i);
+              for (int j = i+1; j < L; j++)
+                { int pos;
+                  if (one_base_apart<KW>(xi,xil,__ldg(keys+h+j),KW == 2 ? __ldg(keys_lo+h+j) : 0,pos) &&
+                      ci + (int) __ldg(cnt+h+j) <= HM_SMAX)
+                    { H += (1u << (4*i)) + (1u << (4*j));
+                      if (pos >= pup) U += (1u << (4*i)) + (1u << (4*j));
+                      PT = (PT & ~((7u << (3*i)) | (7u << (3*j)))) | ((uint32_t) j << (3*i)) | ((uint32_t) i << (3*j));
+                      PP = (PP & ~(((uint64_t) 255 << (8*i)) | ((uint64_t) 255 << (8*j)))) |
+                           ((uint64_t) pos << (8*i)) | ((uint64_t) pos << (8*j));
+                    }
+                }
             }
-          if (Hy == 1)
-            { emit = true;
-              meta = pack_meta(cx,cy,ppos,base_at<KW>(y,yl,ppos));
+          for (int i = 0; i < L; i++)
+            { const int64_t g = h+i;
+              if (g < lo || g >= hi) continue;
+              if (((U >> (4*i)) & 15) != 0)
+                bloom_insert<KW>(W,kmer,__ldg(keys+g),KW == 2 ? __ldg(keys_lo+g) : 0);
+              const int j = (int) ((PT >> (3*i)) & 7);
+              if (((H >> (4*i)) & 15) == 1 && j > i && ((H >> (4*j)) & 15) == 1)
+                nrec += 1;
             }
         }
-    }
-  else                                                 /* the run leaves the window: per-candidate look-ups */
-    { int64_t part;
-      neighbours_slow<IdxT,KW>(keys,keys_lo,cnt,bucket,bshift,kmer,Pr,pup,x,xl,cx,H,U,part,ppos);
-      insert = (U > 0);
-      if (H == 1 && part > g)
-        { uint64_t y = __ldg(keys+part), yl = KW == 2 ? __ldg(keys_lo+part) : 0;
-          const int cy = __ldg(cnt+part);
-          int Hy, Uy, py; int64_t party;
-          neighbours_slow<IdxT,KW>(keys,keys_lo,cnt,bucket,bshift,kmer,Pr,pup,y,yl,cy,Hy,Uy,party,py);
-          if (Hy == 1)
-            { emit = true;
-              meta = pack_meta(cx,cy,ppos,base_at<KW>(y,yl,ppos));
+      /* candidate records of the short runs: one global atomic per warp */
+      { int pre = nrec;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+          { int v = __shfl_up_sync(FULL,pre,o);
+            if (lane >= o) pre += v;
+          }
+        const int tot = __shfl_sync(FULL,pre,31);
+        if (tot > 0)
+          { unsigned long long base = 0;
+            if (lane == 0)
+              base = atomicAdd(W.cand_n,(unsigned long long) tot);
+            base = __shfl_sync(FULL,base,0) + (unsigned long long) (pre-nrec);
+            if (nrec > 0)
+              for (int i = 0; i < L; i++)
+                { const int64_t g = h+i;
+                  if (g < lo || g >= hi) continue;
+                  const int j = (int) ((PT >> (3*i)) & 7);
+                  if (((H >> (4*i)) & 15) == 1 && j > i && ((H >> (4*j)) & 15) == 1)
+                    { const int      pos = (int) ((PP >> (8*i)) & 255);
+                      const uint64_t y = __ldg(keys+h+j), yl = KW == 2 ? __ldg(keys_lo+h+j) : 0;
+                      if (base < W.cand_cap)
+                        { W.cand_key[base] = __ldg(keys+g);
+                          if (KW == 2) W.cand_lo[base] = __ldg(keys_lo+g);
+                          W.cand_meta[base] = pack_meta(__ldg(cnt+g),__ldg(cnt+h+j),pos,base_at<KW>(y,yl,pos));
+                        }
+                      else
+                        atomicOr(W.status,SY_STATUS_OVERFLOW);
+                      base += 1;
+                    }
+                }
+          }
+      }
+      /* ---- long runs: the whole warp, one after the other ---- */
+      unsigned lb = __ballot_sync(FULL,islong);
+      while (lb != 0)
+        { const int     src = __ffs(lb)-1;
+          lb &= lb-1;
+          const int64_t hh = __shfl_sync(FULL,h,src);
+          const uint64_t xx = __shfl_sync(FULL,x0,src);
+          int64_t end = hh+9;                          /* entries hh .. hh+8 are known to be in the run */
+          while (true)
+            { const int64_t t = end+lane;
+              const bool same = (t < n) && (((__ldg(keys+t) ^ xx) & pmask) == 0);
+              const unsigned sb = __ballot_sync(FULL,same);
+              if (sb == FULL) { end += 32; continue; }
+              end += __ffs(~sb)-1;
+              break;
+            }
+          for (int64_t g0 = hh; g0 < end; g0 += 32)
+            { const int64_t g = g0+lane;
+              bool     emit = false;
+              uint64_t x = 0, xl = 0, meta = 0;
+              if (g < end && g >= lo && g < hi)
+                { x = __ldg(keys+g);
+                  if (KW == 2) xl = __ldg(keys_lo+g);
+                  const int cx = __ldg(cnt+g);
+                  int Hn, Un, ppos; int64_t part;
+                  neighbours_slow<IdxT,KW>(keys,keys_lo,cnt,bucket,bshift,kmer,Pr,pup,x,xl,cx,Hn,Un,part,ppos);
+                  if (Un > 0)
+                    bloom_insert<KW>(W,kmer,x,xl);
+                  if (Hn == 1 && part > g)
+                    { const uint64_t y = __ldg(keys+part), yl = KW == 2 ? __ldg(keys_lo+part) : 0;
+                      const int cy = __ldg(cnt+part);
+                      int Hy, Uy, py; int64_t party;
+                      neighbours_slow<IdxT,KW>(keys,keys_lo,cnt,bucket,bshift,kmer,Pr,pup,y,yl,cy,Hy,Uy,party,py);
+                      if (Hy == 1)
+                        { emit = true;
+                          meta = pack_meta(cx,cy,ppos,base_at<KW>(y,yl,ppos));
+                        }
+                    }
+                }
+              const unsigned eb = __ballot_sync(FULL,emit);
+              if (eb != 0)
+                { unsigned long long base = 0;
+                  if (lane == 0)
+                    base = atomicAdd(W.cand_n,(unsigned long long) __popc(eb));
+                  base = __shfl_sync(FULL,base,0) + (unsigned long long) __popc(eb & lt);
+                  if (emit)
+                    { if (base < W.cand_cap)
+                        { W.cand_key[base] = x;
+                          if (KW == 2) W.cand_lo[base] = xl;
+                          W.cand_meta[base] = meta;
+                        }
+                      else
+                        atomicOr(W.status,SY_STATUS_OVERFLOW);
+                    }
+                }
             }
         }
     }
@@ -463,36 +510,41 @@ __device__ __noinline__ void member_of_long_run(const RsSmem<KW> &S, int w, int 
 
 /* Pass 1.  83 % of the entries of a genome-sized table are alone in their run (no other entry shares
  * their first k/2 bases) and 15 % sit in a run of exactly two -- almost always the two alleles of one
- * heterozygous site.  The kernel is bound by instruction issue, not by bytes (55 warp instructions per
- * 32 entries is all a B200 can issue while HBM delivers them), so the common cases are kept loop-free:
- *   1. adjacency bits: eq[i] = slots i, i+1 belong to one run             (one ballot per 32 slots)
- *   2. classification of 8 x 32 entries per warp with bit operations, one WORD PER LANE:
- *      head of a two-entry run / first member of a longer run / nothing
+ * heterozygous site.  The kernel is bound by instruction issue and by the latency of its few serial
+ * phases, not by bytes (55 warp instructions per 32 entries is all a B200 can issue while HBM delivers
+ * them), so the common cases are loop-free and, once the tile has landed, every WARP works on its own
+ * 256 entries without any CTA barrier:
+ *   1. adjacency bits: eq[i] = slots i, i+1 belong to one run (one ballot per 32 slots; a warp computes
+ *      the ten words it needs itself and keeps them one per lane)
+ *   2. classification of 8 x 32 entries with bit operations, one WORD PER LANE:
+ *      head of a two-entry run / head of a longer run / nothing
  *   3. two-entry runs: one comparison settles both members (per-warp task list, every lane busy)
- *   4. longer runs: one thread per run, all pairs once (short_run); members of runs of more than 8
- *      one by one (member_of_long_run)
+ *   4. heads of longer runs are only LISTED (1-2 % of the entries, irregular work): runs_kernel
+ *      takes them one per thread afterwards
+ *   5. candidate records and run heads are staged in shared memory; the LAST warp to finish moves
+ *      them out with one global atomic per CTA and list (one per record, or per warp, on the one
+ *      list counter serialises in L2: 9.2 ms for 1.8e7 records)
  * (Scanning every entry's run in place cost 436 warp instructions per 32 entries at 34 % lane
- * utilisation; per-entry classification with predicated list writes still 163.)                   */
+ * utilisation; per-entry classification with predicated list writes 163; CTA-wide task lists with a
+ * barrier per phase 117, but 57 % of the stall samples at those barriers; longer runs handled by
+ * single lanes of every warp in place: slower again.)                                               */
 template <typename IdxT, int KW>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS,RS_MINBLOCKS)
 runscan_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ keys_lo,
                const uint16_t *__restrict__ cnt, int64_t n, const IdxT *__restrict__ bucket, int bshift,
                int kmer, int64_t lo, int64_t hi, int64_t tile0, int use_tma, const SymmView W)
 { extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t s_bar;
-  __shared__ unsigned s_nc, s_n2r, s_n2m;
-  __shared__ unsigned s_eq[RS_WIN/32];
-  __shared__ unsigned long long s_base;
+  __shared__ unsigned s_nc, s_nr, s_done;
   RsSmem<KW> S;
-  S.key   = (uint64_t *) smem;                               /* RS_WIN+2 slots each (spare: sentinel) */
-  S.klo   = S.key + (KW == 2 ? RS_WIN+2 : 0);
-  S.ckey  = S.key + KW*(RS_WIN+2);
+  S.key   = (uint64_t *) smem;
+  S.klo   = S.key + (KW == 2 ? RS_WIN : 0);
+  S.ckey  = S.key + KW*RS_WIN;
   S.clo   = S.ckey + (KW == 2 ? RS_STAGE : 0);
   S.cmeta = S.ckey + KW*RS_STAGE;
   S.cnt   = (uint16_t *) (S.cmeta + RS_STAGE);
-  S.t1    = S.cnt + RS_WIN+8;
-  S.t2r   = S.t1 + RS_TILE/2;
-  S.t2m   = S.t2r + RS_TILE/2;
+  S.t1    = S.cnt + RS_WIN;                          /* per warp: RS_TILE/2/8 heads of two-entry runs        */
+  S.t2r   = S.t1 + RS_TILE/2;                        /* CTA: heads of longer runs (at most RS_TILE/3)        */
 
   const int      Pr   = kmer >> 1;                 /* run = entries sharing their first Pr bases     */
   const int      pup  = kmer - Pr;                 /* positions >= pup have a mirror position < Pr   */
@@ -513,7 +565,7 @@ runscan_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ k
   const int m   = v1-v0;
   const int mt  = use_tma ? (m & ~7) : 0;
   if (threadIdx.x == 0)
-    { s_nc = 0; s_n2r = 0; s_n2m = 0;
+    { s_nc = 0; s_nr = 0; s_done = 0;
       if (mt > 0)
         { mbar_init(&s_bar,1);
           fence_proxy_async_smem();
@@ -527,27 +579,32 @@ runscan_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ k
         bulk_copy_g2s(S.klo+v0,keys_lo+e0,(unsigned) (8*mt),&s_bar);
       bulk_copy_g2s(S.cnt+v0,cnt+e0,(unsigned) (2*mt),&s_bar);
     }
-  for (int j = mt + threadIdx.x; j < m; j += RS_THREADS)
-    { S.key[v0+j] = keys[e0+j];
-      if (KW == 2) S.klo[v0+j] = keys_lo[e0+j];
-      S.cnt[v0+j] = cnt[e0+j];
-    }
-  if (mt > 0)
-    mbar_wait(&s_bar,0);
-  __syncthreads();
-  /* slots outside the table (first / last tile): a key no neighbour can share a run with */
-  if (v0 > 0 || v1 < RS_WIN)
-    { const uint64_t sa = ~S.key[v0], sb = ~S.key[v1-1];
+  if (mt < m || v0 > 0 || v1 < RS_WIN)                /* boundary tiles / unaligned tables only (CTA-uniform) */
+    { for (int j = mt + threadIdx.x; j < m; j += RS_THREADS)
+        { S.key[v0+j] = keys[e0+j];
+          if (KW == 2) S.klo[v0+j] = keys_lo[e0+j];
+          S.cnt[v0+j] = cnt[e0+j];
+        }
+      if (mt > 0)
+        mbar_wait(&s_bar,0);
+      __syncthreads();
+      /* slots outside the table: a key no neighbour can share a run with */
+      const uint64_t sa = ~S.key[v0], sb = ~S.key[v1-1];
       __syncthreads();
       for (int j = threadIdx.x; j < RS_WIN; j += RS_THREADS)
         if (j < v0)       S.key[j] = sa;
         else if (j >= v1) S.key[j] = sb;
       __syncthreads();
     }
+  else
+    mbar_wait(&s_bar,0);
 
-  /* ---- 1. adjacency bits ---- */
-  for (int wd = 1+warp; wd < RS_WIN/32-1; wd += RS_THREADS/32)       /* (the outermost two words are never looked at) */
-    { const int i = wd*32 + lane;
+  /* ---- 1. adjacency bits of this warp's words wd0-1 .. wd0+RS_EPT, word t in lane t ---- */
+  const int wd0 = RS_HALO/32 + warp*RS_EPT;            /* first word (32 slots) of this warp's part of the tile */
+  unsigned  eqw = 0;
+#pragma unroll
+  for (int t = 0; t < RS_EPT+2; t++)
+    { const int i = (wd0-1+t)*32 + lane;
       bool eq;
       if (psh >= 32)                                   /* k <= 33: the first Pr bases sit in the upper word */
         { const uint32_t a = (uint32_t) (S.key[i] >> 32);
@@ -558,50 +615,52 @@ runscan_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ k
       else
         eq = (((S.key[i] ^ S.key[i+1]) & pmask) == 0);
       const unsigned bal = __ballot_sync(FULL,eq);
-      if (lane == 0)
-        s_eq[wd] = bal;
+      if (lane == t) eqw = bal;
     }
-  __syncthreads();
 
-  /* ---- 2. classify: lane e < RS_EPT takes the e-th of this warp's words of the tile ---- */
+  /* ---- 2. classify: lane t in 1..RS_EPT takes word wd0-1+t ---- */
   const int a0 = RS_HALO + (lo > T0 ? (int) (lo-T0 < RS_TILE ? lo-T0 : RS_TILE) : 0);   /* slots this CTA answers for */
   const int a1 = RS_HALO + (hi-T0 < RS_TILE ? (int) (hi-T0) : RS_TILE);
-  uint16_t *my1 = S.t1 + warp*(RS_TILE/2/(RS_THREADS/32));
+  uint16_t *my1  = S.t1  + warp*(RS_TILE/2/(RS_THREADS/32));
   int n1;
-  { unsigned m2 = 0, m3 = 0;
-    const int wd = RS_HALO/32 + warp*RS_EPT + lane;
-    if (lane < RS_EPT)
-      { const unsigned E = s_eq[wd], P = s_eq[wd-1], N = s_eq[wd+1];
+  { const unsigned P = __shfl_up_sync(FULL,eqw,1), N = __shfl_down_sync(FULL,eqw,1);
+    unsigned m2 = 0, m3 = 0;
+    const int wd = wd0-1+lane;
+    if (lane >= 1 && lane <= RS_EPT)
+      { const unsigned E = eqw;
         const unsigned em1 = (E << 1) | (P >> 31);                     /* eq[w-1] */
         const unsigned em2 = (E << 2) | (P >> 30);                     /* eq[w-2] */
         const unsigned ep1 = (E >> 1) | (N << 31);                     /* eq[w+1] */
         const int      s0  = wd*32;                                    /* slot of bit 0 */
-        unsigned act = 0xffffffffu, actp;                              /* actp: is slot-1 answered for, too? */
+        unsigned act = 0xffffffffu;
         if (s0 < a0)      act &= (a0-s0 >= 32) ? 0u : (0xffffffffu << (a0-s0));
         if (s0+32 > a1)   act &= (a1-s0 <= 0)  ? 0u : (0xffffffffu >> (s0+32-a1));
-        actp = (act << 1) | ((s0-1 >= a0 && s0-1 < a1) ? 1u : 0u);
         const unsigned more = (em1 & E) | (E & ep1) | (em1 & em2);
         m2 = (E & ~em1 & ~ep1) & act;                                  /* head of a run of exactly two */
-        m3 = more & act & ~(em1 & actp);                               /* first answered-for member of a longer run */
+        m3 = more & act & ~em1;                                        /* head of a longer run: listed for runs_kernel */
       }
-    /* per-warp list of the two-run heads: exclusive scan of the counts over the RS_EPT lanes */
-    const int c2 = __popc(m2);
-    int pre = c2;
+    /* per-warp task lists: inclusive scans of the counts over the lanes */
+    const int c2 = __popc(m2), c3 = __popc(m3);
+    int pre2 = c2, pre3 = c3;
 #pragma unroll
-    for (int o = 1; o < RS_EPT; o <<= 1)
-      { int v = __shfl_up_sync(FULL,pre,o);
-        if (lane >= o) pre += v;
+    for (int o = 1; o <= RS_EPT; o <<= 1)
+      { int v2 = __shfl_up_sync(FULL,pre2,o), v3 = __shfl_up_sync(FULL,pre3,o);
+        if (lane >= o) { pre2 += v2; pre3 += v3; }
       }
-    n1 = __shfl_sync(FULL,pre,RS_EPT-1);
-    int at = pre-c2;
+    n1 = __shfl_sync(FULL,pre2,RS_EPT);
+    const int n3 = __shfl_sync(FULL,pre3,RS_EPT);
+    int at = pre2-c2;
     while (m2 != 0)
       { my1[at++] = (uint16_t) (wd*32 + __ffs(m2)-1);
         m2 &= m2-1;
       }
-    if (m3 != 0)
-      { unsigned at3 = atomicAdd(&s_n2r,(unsigned) __popc(m3));
+    if (n3 > 0)                                          /* (warp-uniform) heads of longer runs: CTA list */
+      { unsigned b3 = 0;
+        if (lane == 0)
+          b3 = atomicAdd(&s_nr,(unsigned) n3);
+        at = (int) __shfl_sync(FULL,b3,0) + pre3-c3;
         while (m3 != 0)
-          { S.t2r[at3++] = (uint16_t) (wd*32 + __ffs(m3)-1);
+          { S.t2r[at++] = (uint16_t) (wd*32 + __ffs(m3)-1);
             m3 &= m3-1;
           }
       }
@@ -632,51 +691,39 @@ runscan_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ k
         }
       stage_candidates<KW>(S,&s_nc,W,emit,x,xl,meta,lane,lt);
     }
-  __syncthreads();
 
-  /* ---- 4. longer runs: one thread per run; members of runs of more than 8 go to the second list ---- */
-  const int n2r = (int) s_n2r;
-  for (int i = threadIdx.x; i < n2r; i += RS_THREADS)
-    { const int w = S.t2r[i];
-      int b0, b1;
-      if (!short_run<KW>(S,&s_nc,W,w,a0,a1,pmask,kmer,b0,b1))
-        { /* hand every answered-for member from w to the end of the run (or of the tile) to the list */
-          const uint64_t x0 = S.key[w];
-          for (int j = w; j < a1 && ((S.key[j] ^ x0) & pmask) == 0; j++)
-            S.t2m[atomicAdd(&s_n2m,1u)] = (uint16_t) j;
-        }
+  /* ---- 5. the last warp to get here moves the staged records out ---- */
+  __syncwarp();
+  unsigned last = 0;
+  if (lane == 0)
+    { __threadfence_block();
+      last = (atomicAdd(&s_done,1u) == RS_THREADS/32-1);
     }
-  __syncthreads();
-  const int n2m = (int) s_n2m;
-  if (n2m > 0)
-    { for (int i0 = (threadIdx.x & ~31); i0 < n2m; i0 += RS_THREADS)
-        { const int i = i0+lane;
-          bool     emit = false, insert = false;
-          uint64_t x = 0, xl = 0, meta = 0;
-          if (i < n2m)
-            { const int w = S.t2m[i];
-              x = S.key[w];
-              if (KW == 2) xl = S.klo[w];
-              member_of_long_run<IdxT,KW>(S,w,v0,v1,e0,e1,n,T0+(w-RS_HALO),kmer,keys,keys_lo,cnt,bucket,bshift,
-                                          insert,emit,meta);
-            }
-          if (insert)
-            bloom_insert<KW>(W,kmer,x,xl);
-          stage_candidates<KW>(S,&s_nc,W,emit,x,xl,meta,lane,lt);
-        }
-      __syncthreads();
+  last = __shfl_sync(FULL,last,0);
+  if (!last)
+    return;
+  __threadfence_block();
+  const unsigned nr = s_nr;
+  if (nr > 0)
+    { unsigned long long rb = 0;
+      if (lane == 0)
+        rb = atomicAdd(W.runs_n,(unsigned long long) nr);
+      rb = __shfl_sync(FULL,rb,0);
+      for (unsigned i = lane; i < nr; i += 32)
+        if (rb+i < W.runs_cap)
+          W.runs[rb+i] = (uint64_t) (T0 + ((int) S.t2r[i] - RS_HALO));
+        else
+          atomicOr(W.status,SY_STATUS_OVERFLOW);
     }
-
-  /* ---- the staged records leave the CTA in one piece: one global atomic per CTA (one per record, or
-   *      per warp, on the one list counter serialises in L2: 9.2 ms for 1.8e7 records)            ---- */
   const unsigned nc = s_nc < RS_STAGE ? s_nc : RS_STAGE;
   if (nc == 0)
     return;
-  if (threadIdx.x == 0)
-    s_base = atomicAdd(W.cand_n,(unsigned long long) nc);
-  __syncthreads();
-  for (unsigned i = threadIdx.x; i < nc; i += RS_THREADS)
-    { unsigned long long at = s_base + i;
+  unsigned long long base = 0;
+  if (lane == 0)
+    base = atomicAdd(W.cand_n,(unsigned long long) nc);
+  base = __shfl_sync(FULL,base,0);
+  for (unsigned i = lane; i < nc; i += 32)
+    { unsigned long long at = base + i;
       if (at < W.cand_cap)
         { W.cand_key[at] = S.ckey[i];
           if (KW == 2) W.cand_lo[at] = S.clo[i];
@@ -692,8 +739,8 @@ static cudaError_t launch_runscan(const uint64_t *keys, const uint64_t *keys_lo,
                                   const void *bucket, int bits, int kmer, int64_t lo, int64_t hi,
                                   const SymmView &W, cudaStream_t st)
 { static int configured[64] = {0};                            /* per instantiation */
-  size_t smem = (size_t) (RS_WIN+2)*8*KW + (size_t) (RS_WIN+8)*2 + (size_t) RS_STAGE*8*(KW+1) +
-                2*(size_t) (RS_TILE/2+RS_TILE/2+RS_TILE);                            /* 38 KB (k <= 32) / 59 KB */
+  size_t smem = (size_t) RS_WIN*(8*KW+2) + (size_t) RS_STAGE*8*(KW+1) +
+                2*(size_t) (RS_TILE/2+RS_TILE/2);                                    /* 34 KB (k <= 32) / 55 KB */
   int dev = 0;
   cudaGetDevice(&dev);
   if (smem > 48*1024 && (dev >= 64 || !configured[dev]))
@@ -705,6 +752,13 @@ static cudaError_t launch_runscan(const uint64_t *keys, const uint64_t *keys_lo,
   int     tma   = ((((uintptr_t) keys) | ((uintptr_t) cnt) | ((uintptr_t) (keys_lo ? keys_lo : keys))) & 15) == 0;
   runscan_kernel<IdxT,KW><<<(unsigned) (tile1-tile0),RS_THREADS,smem,st>>>
       (keys,keys_lo,cnt,n,(const IdxT *) bucket,64-bits,kmer,lo,hi,tile0,tma,W);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms,cudaDevAttrMultiProcessorCount,dev);
+  int64_t want = ((hi-lo)/64+255)/256;                        /* ~1 run of three or more per 60 entries */
+  int     grid = (int) (want < sms*8 ? (want > 0 ? want : 1) : sms*8);
+  runs_kernel<IdxT,KW><<<grid,256,0,st>>>(keys,keys_lo,cnt,n,(const IdxT *) bucket,64-bits,kmer,lo,hi,W);
   return cudaGetLastError();
 }
 
@@ -744,10 +798,11 @@ extern "C" int hm_k_symm_runscan(const uint64_t *d_keys, const uint64_t *d_keys_
 
 /* ------------------------------------------------------------------------ pass 2 -------- */
 
-#define RV_TS 192      /* shared-memory plot tile: sums < 192, mins < 88 (66 KB; 3 CTAs per SM with the queues) */
-#define RV_TM 88
+#define RV_TS 192      /* shared-memory plot tile: sums < 192, mins < 96 (72 KB) */
+#define RV_TM 96
 #define RV_THREADS 512
-#define RV_CTAS_PER_SM 3
+#define RV_CTAS_PER_SM 2
+#define RV_ILP 4
 
 /* does table entry q (count cq: the table is symmetric, so it is the count of the candidate member
  * whose reverse complement q is) have a partner at a position >= pup?  Exact.  The bucket index is at
@@ -847,17 +902,18 @@ __device__ __forceinline__ void count_pair(uint32_t *tile, unsigned long long *_
     atomicAdd(plot + s*HM_PLOT_W + m, (unsigned long long) wgt);
 }
 
-/* Candidates whose Bloom look-ups both miss (~85 %) are counted at once.  The others need the exact
- * answer -- a bucket look-up and a run scan per hit, ~5 dependent random accesses -- and a warp in
- * which one lane does that stalls all 32: they are parked in a per-warp queue and settled 32 at a
- * time, every lane busy.                                                                           */
+/* Candidates whose Bloom look-up misses (~95 %) are counted at once.  The others need the exact
+ * answer -- bucket offsets, keys, counts: three dependent random accesses -- and a warp in which one
+ * lane does that stalls all 32: they are parked in a per-warp queue and settled 32 at a time, every
+ * lane busy.  RV_ILP candidates per thread and trip keep that many record / Bloom loads in flight
+ * (the kernel is bound by the latency of record -> Bloom word, not by bytes or instructions).         */
 template <typename IdxT, int KW>
 __global__ void __launch_bounds__(RV_THREADS,RV_CTAS_PER_SM)
 resolve_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ keys_lo,
                const uint16_t *__restrict__ cnt, int64_t n, const IdxT *__restrict__ bucket, int bshift,
                int kmer, const SymmView W, unsigned long long *__restrict__ plot)
 { extern __shared__ uint32_t tile[];
-  __shared__ uint32_t s_q[RV_THREADS/32][64];
+  __shared__ uint32_t s_q[RV_THREADS/32][32*(RV_ILP+1)];
   const unsigned FULL = 0xffffffffu;
   const int      lane = threadIdx.x & 31;
   const unsigned lt   = (1u << lane) - 1;
@@ -871,38 +927,66 @@ resolve_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ k
   const int64_t nc     = (int64_t) ncl;
   const int64_t stride = (int64_t) gridDim.x * blockDim.x;
   const int64_t first  = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-  for (uint32_t it = 0; first-lane + (int64_t) it*stride < nc; it++)
-    { const int64_t i = first + (int64_t) it*stride;
-      bool pend = false;
-      if (i < nc)
-        { const uint64_t x = ld_stream(W.cand_key+i), xl = KW == 2 ? ld_stream(W.cand_lo+i) : 0,
-                         meta = ld_stream(W.cand_meta+i);
-          int v = judge_candidate<IdxT,KW,false>(keys,keys_lo,cnt,n,bucket,bshift,kmer,W,x,xl,meta);
-          if (v == 0)
-            count_pair(tile,plot,meta,kmer);
-          pend = (v == 2);
+  for (uint32_t it = 0; first-lane + (int64_t) it*RV_ILP*stride < nc; it++)
+    { uint64_t x[RV_ILP], xl[RV_ILP], meta[RV_ILP];
+      uint32_t *wa[RV_ILP], *wb[RV_ILP], ba[RV_ILP], bb[RV_ILP], va[RV_ILP], vb[RV_ILP];
+      bool     ok[RV_ILP];
+#pragma unroll
+      for (int u = 0; u < RV_ILP; u++)
+        { const int64_t i = first + ((int64_t) it*RV_ILP+u)*stride;
+          ok[u] = (i < nc);
+          x[u] = 0; xl[u] = 0; meta[u] = 0;
+          if (ok[u])
+            { x[u] = ld_stream(W.cand_key+i);
+              if (KW == 2) xl[u] = ld_stream(W.cand_lo+i);
+              meta[u] = ld_stream(W.cand_meta+i);
+            }
         }
-      const unsigned bal = __ballot_sync(FULL,pend);
-      if (pend)
-        q[qn + __popc(bal & lt)] = (it << 5) | (uint32_t) lane;
-      qn += __popc(bal);
+#pragma unroll
+      for (int u = 0; u < RV_ILP; u++)
+        { const int p  = (int) ((meta[u] >> 32) & 0xff), yb = (int) ((meta[u] >> 40) & 3);
+          uint64_t rx, rxl, ry, ryl;
+          revcomp_kmer<KW>(x[u],xl[u],kmer,rx,rxl);
+          ry = rx; ryl = rxl;
+          set_base<KW>(ry,ryl,kmer-1-p,3-yb);
+          bloom_slot<KW>(W,W.n_seg > 1 ? owner_of(W,rx) : 0,kmer,rx,rxl,wa[u],ba[u]);
+          bloom_slot<KW>(W,W.n_seg > 1 ? owner_of(W,ry) : 0,kmer,ry,ryl,wb[u],bb[u]);
+        }
+#pragma unroll
+      for (int u = 0; u < RV_ILP; u++)
+        { va[u] = 0; vb[u] = 0;
+          if (ok[u])
+            { va[u] = ld_keep(wa[u]);
+              vb[u] = (wb[u] == wa[u]) ? va[u] : ld_keep(wb[u]);
+            }
+        }
+#pragma unroll
+      for (int u = 0; u < RV_ILP; u++)
+        { const bool hit = ok[u] && ((va[u] & ba[u]) == ba[u] || (vb[u] & bb[u]) == bb[u]);
+          if (ok[u] && !hit)
+            count_pair(tile,plot,meta[u],kmer);
+          const unsigned bal = __ballot_sync(FULL,hit);
+          if (hit)
+            q[qn + __popc(bal & lt)] = ((it*RV_ILP+u) << 5) | (uint32_t) lane;
+          qn += __popc(bal);
+        }
       __syncwarp();
-      if (qn >= 32)
+      while (qn >= 32)
         { qn -= 32;
           const uint32_t e = q[qn+lane];
           __syncwarp();
           const int64_t j = first-lane + (int64_t) (e & 31) + (int64_t) (e >> 5)*stride;
-          const uint64_t x = W.cand_key[j], xl = KW == 2 ? W.cand_lo[j] : 0, meta = W.cand_meta[j];
-          if (judge_candidate<IdxT,KW,true>(keys,keys_lo,cnt,n,bucket,bshift,kmer,W,x,xl,meta) == 0)
-            count_pair(tile,plot,meta,kmer);
+          const uint64_t xx = W.cand_key[j], xxl = KW == 2 ? W.cand_lo[j] : 0, mm = W.cand_meta[j];
+          if (judge_candidate<IdxT,KW,true>(keys,keys_lo,cnt,n,bucket,bshift,kmer,W,xx,xxl,mm) == 0)
+            count_pair(tile,plot,mm,kmer);
         }
     }
   if (lane < qn)
     { const uint32_t e = q[lane];
       const int64_t j = first-lane + (int64_t) (e & 31) + (int64_t) (e >> 5)*stride;
-      const uint64_t x = W.cand_key[j], xl = KW == 2 ? W.cand_lo[j] : 0, meta = W.cand_meta[j];
-      if (judge_candidate<IdxT,KW,true>(keys,keys_lo,cnt,n,bucket,bshift,kmer,W,x,xl,meta) == 0)
-        count_pair(tile,plot,meta,kmer);
+      const uint64_t xx = W.cand_key[j], xxl = KW == 2 ? W.cand_lo[j] : 0, mm = W.cand_meta[j];
+      if (judge_candidate<IdxT,KW,true>(keys,keys_lo,cnt,n,bucket,bshift,kmer,W,xx,xxl,mm) == 0)
+        count_pair(tile,plot,mm,kmer);
     }
   __syncthreads();
   for (int t = threadIdx.x; t < RV_TS*RV_TM; t += blockDim.x)
