@@ -90,9 +90,10 @@ __device__ __forceinline__ void bloom_slot(const SymmView &W, int seg, int kmer,
   if (2*Pr < 64)
     sfx &= (((uint64_t) 1 << (2*Pr)) - 1);
   const uint64_t pfx = hi >> (64-2*pup);                       /* the first pup <= 32 bases */
-  const uint32_t h = (uint32_t) ((sfx * 0x9E3779B97F4A7C15ull) >> 32);
-  const uint32_t g = (uint32_t) ((pfx * 0xD6E8FEB86659FD93ull) >> 32);
-  word = W.bloom + (size_t) seg * W.seg_words + __umulhi(h,W.seg_words);
+  uint32_t h = ((uint32_t) sfx ^ (uint32_t) (sfx >> 32) * 0x85EBCA6Bu) * 0x9E3779B1u;     /* 32-bit mixing is plenty here */
+  uint32_t g = ((uint32_t) pfx ^ (uint32_t) (pfx >> 32) * 0xC2B2AE35u) * 0x27D4EB2Fu;
+  h ^= h >> 15;
+  word = W.bloom + (size_t) seg * W.seg_words + __umulhi(h * 0x2C1B3C6Du,W.seg_words);
   mask = (1u << (g >> 27)) | (1u << ((g >> 22) & 31));
 }
 
@@ -223,8 +224,9 @@ extern "C" void hm_symm_seeds(uint64_t seed[2])
 extern "C" int hm_symm_plan(int64_t n, int64_t range, int kmer, int n_seg, hm_symm_layout *out)
 { if (out == NULL || n < 0 || range < 0 || range > n || n_seg < 1 || n_seg > HM_MAX_SHARDS)
     return hm_set_error(HM_EINVAL,"hm_symm_plan: bad arguments");
-  int bits = 1;                                  /* Bloom bits per table entry (S is ~1/6 of the table; two bits
-                                                  *   set per element): small enough to stay L2 resident          */
+  int bits = 1;                                  /* Bloom bits per table entry (S is ~1/6 of the table; two bits set per
+                                                  *   element): 25 MB at 2e8 entries.  2 bits: fewer exact checks in
+                                                  *   pass 2 (-0.15 ms) but the inserts of pass 1 miss L2 (+0.2 ms)   */
   const char *e = getenv("HETMERS_BLOOM_BITS");
   if (e != NULL && atoi(e) >= 1 && atoi(e) <= 64)
     bits = atoi(e);
@@ -754,10 +756,10 @@ static cudaError_t launch_runscan(const uint64_t *keys, const uint64_t *keys_lo,
       (keys,keys_lo,cnt,n,(const IdxT *) bucket,64-bits,kmer,lo,hi,tile0,tma,W);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms,cudaDevAttrMultiProcessorCount,dev);
-  int64_t want = ((hi-lo)/64+255)/256;                        /* ~1 run of three or more per 60 entries */
-  int     grid = (int) (want < sms*8 ? (want > 0 ? want : 1) : sms*8);
+  /* (building the Bloom filter from the record list in a kernel of its own instead of inside runscan_kernel
+   *  was measured slower: +0.15 ms)                                                                        */
+  int64_t want = ((hi-lo)/64+255)/256;                        /* ~1 run of three or more per 60 entries: a thread each */
+  int     grid = (int) (want < 0x7fffffff ? (want > 0 ? want : 1) : 0x7fffffff);
   runs_kernel<IdxT,KW><<<grid,256,0,st>>>(keys,keys_lo,cnt,n,(const IdxT *) bucket,64-bits,kmer,lo,hi,W);
   return cudaGetLastError();
 }
