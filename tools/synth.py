@@ -130,14 +130,14 @@ def synth_table(k: int, G: int, ploidy: int = 2, het: float = 0.01, cov: float =
             v = (v << 2) | b[j:j + n_k]
         if k < 32:
             v = v << (64 - 2 * k)
-        chunks.append(v)
-        chunks.append(revcomp_left(v, k))
-        del v
+        for w in (v, revcomp_left(v, k)):          # a rank's shard: filter before concatenating (memory)
+            if key_range is not None:
+                pre = _lsr(w, 40)
+                w = w[(pre >= key_range[0]) & (pre < key_range[1])]
+            chunks.append(w)
+        del v, w
     allk = torch.cat(chunks)
     del chunks
-    if key_range is not None:
-        pre = _lsr(allk, 40)
-        allk = allk[(pre >= key_range[0]) & (pre < key_range[1])]
     keys, occ = torch.unique(allk ^ _SIGN, sorted=True, return_counts=True)
     keys = keys ^ _SIGN
     del allk
