@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
+#include <pthread.h>
 
 #include "hetmers_b200.h"
 #include "hm_internal.h"
@@ -26,24 +27,53 @@
 typedef struct { uint32_t *p[PEER_MAX]; } DegPtrs;
 typedef struct { unsigned long long *p[PEER_MAX]; } PlotPtrs;
 
-int hm_peer_enable(const int *dev, int n)
-{ for (int a = 0; a < n; a++)
-    { int da = dev ? dev[a] : a;
-      HM_CUDA(cudaSetDevice(da));
-      for (int b = 0; b < n; b++)
-        { int db = dev ? dev[b] : b, can = 0;
-          if (da == db) continue;
-          HM_CUDA(cudaDeviceCanAccessPeer(&can,da,db));
-          if (!can)
-            return hm_set_error(HM_ECUDA,"GPU %d cannot access GPU %d's memory (no NVLink/P2P)",da,db);
-          cudaError_t e = cudaDeviceEnablePeerAccess(db,0);
-          if (e == cudaErrorPeerAccessAlreadyEnabled)
-            cudaGetLastError();
-          else if (e != cudaSuccess)
-            return hm_cuda_fail(e,"cudaDeviceEnablePeerAccess");
-        }
+typedef struct { const int *dev; int n, a, rc; char msg[256]; } PeerJob;
+
+static int peer_enable_one(const int *dev, int n, int a)
+{ int da = dev ? dev[a] : a;
+  HM_CUDA(cudaSetDevice(da));
+  for (int b = 0; b < n; b++)
+    { int db = dev ? dev[b] : b, can = 0;
+      if (da == db) continue;
+      HM_CUDA(cudaDeviceCanAccessPeer(&can,da,db));
+      if (!can)
+        return hm_set_error(HM_ECUDA,"GPU %d cannot access GPU %d's memory (no NVLink/P2P)",da,db);
+      cudaError_t e = cudaDeviceEnablePeerAccess(db,0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled)
+        cudaGetLastError();
+      else if (e != cudaSuccess)
+        return hm_cuda_fail(e,"cudaDeviceEnablePeerAccess");
     }
   return HM_OK;
+}
+
+static void *peer_worker(void *arg)
+{ PeerJob *J = (PeerJob *) arg;
+  J->rc = peer_enable_one(J->dev,J->n,J->a);
+  if (J->rc != HM_OK)
+    { strncpy(J->msg,hm_last_error(),sizeof(J->msg)-1); J->msg[sizeof(J->msg)-1] = 0; }
+  return NULL;
+}
+
+/* every GPU maps every other GPU's memory: n*(n-1) driver calls, one host thread per GPU */
+int hm_peer_enable(const int *dev, int n)
+{ PeerJob   job[PEER_MAX];
+  pthread_t th[PEER_MAX];
+  int       made[PEER_MAX], rc = HM_OK;
+  if (n > PEER_MAX)
+    return hm_set_error(HM_EINVAL,"at most %d GPUs",PEER_MAX);
+  for (int a = 0; a < n; a++)
+    { job[a].dev = dev; job[a].n = n; job[a].a = a; job[a].rc = HM_OK; job[a].msg[0] = 0;
+      made[a] = (a+1 < n) && (pthread_create(th+a,NULL,peer_worker,job+a) == 0);
+      if (!made[a])
+        peer_worker(job+a);
+    }
+  for (int a = 0; a < n; a++)
+    { if (made[a]) pthread_join(th[a],NULL);
+      if (job[a].rc != HM_OK && rc == HM_OK)
+        rc = hm_set_error(job[a].rc,"%s",job[a].msg);
+    }
+  return rc;
 }
 
 /* ---- CUDA IPC plumbing for the one-process-per-GPU job (layer A callers) ---- */

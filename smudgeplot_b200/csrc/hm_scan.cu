@@ -226,14 +226,27 @@ static int       g_warm_state = 0;            /* 0 idle, 1 running, 2 joined */
 static int       g_warm_ngpu = 1;
 static uint8_t  *g_pin_cache[2] = { NULL, NULL };
 
+static void *warm_one(void *arg)
+{ int g = (int) (intptr_t) arg;
+  if (cudaSetDevice(g) == cudaSuccess)
+    cudaFree(0);                              /* creates the primary context */
+  return NULL;
+}
+
 static void *warm_worker(void *)
 { int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess)
     { cudaGetLastError(); return NULL; }
   int use = (g_warm_ngpu <= 0 || g_warm_ngpu > n) ? n : g_warm_ngpu;
-  for (int g = 0; g < use; g++)
-    if (cudaSetDevice(g) == cudaSuccess)
-      cudaFree(0);                            /* creates the primary context */
+  if (use > HM_MAX_GPUS) use = HM_MAX_GPUS;
+  pthread_t th[HM_MAX_GPUS];
+  int       made[HM_MAX_GPUS];
+  for (int g = 1; g < use; g++)               /* the contexts of several GPUs at once */
+    made[g] = (pthread_create(th+g,NULL,warm_one,(void *) (intptr_t) g) == 0);
+  warm_one((void *) (intptr_t) 0);
+  for (int g = 1; g < use; g++)
+    if (made[g]) pthread_join(th[g],NULL);
+    else         warm_one((void *) (intptr_t) g);
   cudaSetDevice(0);
   for (int i = 0; i < 2; i++)
     if (cudaHostAlloc(&g_pin_cache[i],PIN_CACHE_BYTES,cudaHostAllocDefault) != cudaSuccess)
