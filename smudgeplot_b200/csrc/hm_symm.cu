@@ -50,6 +50,7 @@
 #define RS_HALO    64                          /* entries staged on either side of the tile      */
 #define RS_WIN     (RS_TILE+2*RS_HALO)
 #define RS_SCANCAP RS_HALO                     /* longest run half scanned linearly               */
+#define RS_LONGRUN 32                          /* dense kernel: runs of more entries go to runs_kernel */
 #ifndef RS_MINBLOCKS
 #define RS_MINBLOCKS 5                         /* resident CTAs per SM the register budget must allow          */
 #endif
@@ -736,25 +737,260 @@ runscan_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ k
     }
 }
 
+/* Pass 1, crowded tables.  A run is the set of entries sharing their first k/2 bases, so an entry has
+ * n / 4^(k/2) run mates on average whatever the sequence: 0.19 at 2e8 k-mers of k = 31 (where "alone" and
+ * "a run of two" are all there is and runscan_kernel's classification pays), but 1.9 at 2e9 and 4.7 at
+ * 5e9, where nearly every entry sits in a run of several unrelated k-mers.  Here every window slot
+ * compares itself with the slots AFTER it in its run (the run's extent comes from the adjacency bits),
+ * a pair found adds to both members' partner counts (byte-packed shared-memory atomics) and records the
+ * partner; after a barrier every entry of the tile reads its own counts: Bloom insert if it has an
+ * upper partner, candidate record if it and its single partner have one partner each.  All pairs of a
+ * run are compared exactly once, the comparisons are spread evenly over the lanes, and the cost grows
+ * with the run length instead of falling off a cliff (the one-thread-per-run kernel took 9.2 ms per
+ * 2.5e8 entries at 2e9 k-mers, 377 ms per 6.25e8 at 5e9).  Runs of more than RS_LONGRUN entries are
+ * listed for runs_kernel as before.                                                                   */
+template <typename IdxT, int KW>
+__global__ void __launch_bounds__(RS_THREADS,RS_MINBLOCKS)
+runscan_dense_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ keys_lo,
+                     const uint16_t *__restrict__ cnt, int64_t n, int kmer, int64_t lo, int64_t hi,
+                     int64_t tile0, int use_tma, const SymmView W)
+{ extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ unsigned s_nc, s_nl, s_done;
+  __shared__ unsigned s_eq[RS_WIN/32+1];
+  RsSmem<KW> S;
+  S.key   = (uint64_t *) smem;
+  S.klo   = S.key + (KW == 2 ? RS_WIN : 0);
+  S.ckey  = S.key + KW*RS_WIN;
+  S.clo   = S.ckey + (KW == 2 ? RS_STAGE : 0);
+  S.cmeta = S.ckey + KW*RS_STAGE;
+  S.cnt   = (uint16_t *) (S.cmeta + RS_STAGE);
+  S.t1    = S.cnt + RS_WIN;                          /* here: a mark per window slot (RS_WIN)                */
+  S.t2r   = S.t1 + RS_WIN;                           /* here: heads of runs of more than RS_LONGRUN entries  */
+  uint16_t *s_part = S.t2r + RS_TILE/8;               /* partner slot of every window slot (RS_WIN)           */
+  unsigned *hu = (unsigned *) (s_part + RS_WIN);      /* partner counts: per slot H (low byte) | U (high byte) */
+
+  const int      Pr   = kmer >> 1, pup = kmer - Pr, psh = 64-2*Pr;
+  const uint64_t pmask = ~(uint64_t) 0 << psh;
+  const unsigned FULL = 0xffffffffu;
+  const int      lane = threadIdx.x & 31;
+  const int      warp = threadIdx.x >> 5;
+  const unsigned lt   = (1u << lane) - 1;
+
+  const int64_t T0 = (tile0 + blockIdx.x) * RS_TILE;
+  const int64_t ws = T0 - RS_HALO;
+  const int64_t e0 = ws > 0 ? ws : 0;
+  const int64_t e1 = T0+RS_TILE+RS_HALO < n ? T0+RS_TILE+RS_HALO : n;
+  const int     v0 = (int) (e0-ws), v1 = (int) (e1-ws);
+
+  const int m   = v1-v0;
+  const int mt  = use_tma ? (m & ~7) : 0;
+  if (threadIdx.x == 0)
+    { s_nc = 0; s_nl = 0; s_done = 0;
+      if (mt > 0)
+        { mbar_init(&s_bar,1);
+          fence_proxy_async_smem();
+        }
+    }
+  for (int j = threadIdx.x; j < RS_WIN/2; j += RS_THREADS)
+    hu[j] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0 && mt > 0)
+    { mbar_arrive_expect_tx(&s_bar,(unsigned) (mt*(8*KW+2)));
+      bulk_copy_g2s(S.key+v0,keys+e0,(unsigned) (8*mt),&s_bar);
+      if (KW == 2)
+        bulk_copy_g2s(S.klo+v0,keys_lo+e0,(unsigned) (8*mt),&s_bar);
+      bulk_copy_g2s(S.cnt+v0,cnt+e0,(unsigned) (2*mt),&s_bar);
+    }
+  if (mt < m || v0 > 0 || v1 < RS_WIN)                /* boundary tiles / unaligned tables only (CTA-uniform) */
+    { for (int j = mt + threadIdx.x; j < m; j += RS_THREADS)
+        { S.key[v0+j] = keys[e0+j];
+          if (KW == 2) S.klo[v0+j] = keys_lo[e0+j];
+          S.cnt[v0+j] = cnt[e0+j];
+        }
+      if (mt > 0)
+        mbar_wait(&s_bar,0);
+      __syncthreads();
+      const uint64_t sa = ~S.key[v0], sb = ~S.key[v1-1];
+      __syncthreads();
+      for (int j = threadIdx.x; j < RS_WIN; j += RS_THREADS)
+        if (j < v0)       S.key[j] = sa;
+        else if (j >= v1) S.key[j] = sb;
+      __syncthreads();
+    }
+  else
+    mbar_wait(&s_bar,0);
+
+  /* ---- adjacency bits of the whole window ---- */
+  for (int wd = warp; wd < RS_WIN/32; wd += RS_THREADS/32)
+    { const int i = wd*32 + lane;
+      bool eq = false;
+      if (i+1 < RS_WIN)
+        eq = (((S.key[i] ^ S.key[i+1]) & pmask) == 0);
+      const unsigned bal = __ballot_sync(FULL,eq);
+      if (lane == 0)
+        s_eq[wd] = bal;
+    }
+  if (threadIdx.x == 0)
+    s_eq[RS_WIN/32] = 0;
+  __syncthreads();
+
+  /* ---- every slot against the slots after it in its run ---- */
+  const int a0 = RS_HALO + (lo > T0 ? (int) (lo-T0 < RS_TILE ? lo-T0 : RS_TILE) : 0);   /* slots this CTA answers for */
+  const int a1 = RS_HALO + (hi-T0 < RS_TILE ? (int) (hi-T0) : RS_TILE);
+  for (int i = threadIdx.x; i < RS_WIN; i += RS_THREADS)
+    { /* members after / before slot i = consecutive ones in the adjacency bits (>= 33 of them are in view) */
+      const int      w = i >> 5, b = i & 31;
+      const uint64_t up = ((uint64_t) s_eq[w] | ((uint64_t) s_eq[w+1] << 32)) >> b;      /* eq[i], eq[i+1], ... */
+      const int      f  = __ffsll((long long) ~up);
+      const int      fwd = f ? f-1 : 64;
+      int back = 0;
+      if (i > 0)
+        { const int      wq = (i-1) >> 5, bq = (i-1) & 31;
+          const uint64_t dn = (((uint64_t) s_eq[wq] << 32) | (wq > 0 ? (uint64_t) s_eq[wq-1] : 0)) << (31-bq);
+          back = __clzll((long long) ~dn);                                                 /* eq[i-1], eq[i-2], ... from the top */
+        }
+      uint16_t mark = (uint16_t) i;                                                        /* "no partner yet" */
+      if (back+fwd+1 > RS_LONGRUN)
+        { mark = 0xffff;                                                                   /* member of a long run: not ours */
+          if (back == 0 && i >= a0 && i < a1)                                              /* its head, in our range: runs_kernel */
+            S.t2r[atomicAdd(&s_nl,1u)] = (uint16_t) i;
+        }
+      else if (fwd > 0)
+        mark = (uint16_t) (0x8000 | i);                                                    /* has run mates after it */
+      S.t1[i] = mark;
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < RS_WIN; i += RS_THREADS)
+    { if ((S.t1[i] & 0x8000) == 0 || S.t1[i] == 0xffff)
+        continue;
+      const int      w = i >> 5, b = i & 31;
+      const uint64_t up = ((uint64_t) s_eq[w] | ((uint64_t) s_eq[w+1] << 32)) >> b;
+      const int      fwd = __ffsll((long long) ~up) - 1;
+      const uint64_t x = S.key[i], xl = KW == 2 ? S.klo[i] : 0;
+      const int      cx = S.cnt[i];
+      for (int j = i+1; j <= i+fwd; j++)
+        { int pos;
+          if (one_base_apart<KW>(x,xl,S.key[j],KW == 2 ? S.klo[j] : 0,pos) && cx + (int) S.cnt[j] <= HM_SMAX)
+            { const unsigned inc = 1u | (pos >= pup ? 0x100u : 0u);
+              atomicAdd(hu + (i>>1), inc << (16*(i&1)));
+              atomicAdd(hu + (j>>1), inc << (16*(j&1)));
+              s_part[i] = (uint16_t) j;                    /* any partner: only read when there is exactly one */
+              s_part[j] = (uint16_t) i;
+            }
+        }
+    }
+  __syncthreads();
+
+  /* ---- every entry of the tile: its counts -> Bloom insert, candidate record ---- */
+  for (int i0 = RS_HALO + (threadIdx.x & ~31); i0 < RS_HALO+RS_TILE; i0 += RS_THREADS)
+    { const int i = i0+lane;
+      bool     emit = false;
+      uint64_t x = 0, xl = 0, meta = 0;
+      if (i >= a0 && i < a1 && S.t1[i] != 0xffff)
+        { const unsigned c = (hu[i>>1] >> (16*(i&1))) & 0xffffu;
+          const int H = (int) (c & 0xff), U = (int) (c >> 8);
+          if (H > 0)
+            { x = S.key[i];
+              if (KW == 2) xl = S.klo[i];
+              if (U > 0)
+                bloom_insert<KW>(W,kmer,x,xl);
+              const int j = s_part[i];
+              if (H == 1 && j > i && ((hu[j>>1] >> (16*(j&1))) & 0xffu) == 1)
+                { const uint64_t y = S.key[j], yl = KW == 2 ? S.klo[j] : 0;
+                  int pos;
+                  one_base_apart<KW>(x,xl,y,yl,pos);
+                  emit = true;
+                  meta = pack_meta(S.cnt[i],S.cnt[j],pos,base_at<KW>(y,yl,pos));
+                }
+            }
+        }
+      stage_candidates<KW>(S,&s_nc,W,emit,x,xl,meta,lane,lt);
+    }
+
+  /* ---- the last warp to get here moves the staged records and the long-run heads out ---- */
+  __syncwarp();
+  unsigned last = 0;
+  if (lane == 0)
+    { __threadfence_block();
+      last = (atomicAdd(&s_done,1u) == RS_THREADS/32-1);
+    }
+  last = __shfl_sync(FULL,last,0);
+  if (!last)
+    return;
+  __threadfence_block();
+  const unsigned nr = s_nl;
+  if (nr > 0)
+    { unsigned long long rb = 0;
+      if (lane == 0)
+        rb = atomicAdd(W.runs_n,(unsigned long long) nr);
+      rb = __shfl_sync(FULL,rb,0);
+      for (unsigned i = lane; i < nr; i += 32)
+        if (rb+i < W.runs_cap)
+          W.runs[rb+i] = (uint64_t) (T0 + ((int) S.t2r[i] - RS_HALO));
+        else
+          atomicOr(W.status,SY_STATUS_OVERFLOW);
+    }
+  const unsigned nc = s_nc < RS_STAGE ? s_nc : RS_STAGE;
+  if (nc == 0)
+    return;
+  unsigned long long base = 0;
+  if (lane == 0)
+    base = atomicAdd(W.cand_n,(unsigned long long) nc);
+  base = __shfl_sync(FULL,base,0);
+  for (unsigned i = lane; i < nc; i += 32)
+    { unsigned long long at = base + i;
+      if (at < W.cand_cap)
+        { W.cand_key[at] = S.ckey[i];
+          if (KW == 2) W.cand_lo[at] = S.clo[i];
+          W.cand_meta[at] = S.cmeta[i];
+        }
+      else
+        atomicOr(W.status,SY_STATUS_OVERFLOW);
+    }
+}
+
 template <typename IdxT, int KW>
 static cudaError_t launch_runscan(const uint64_t *keys, const uint64_t *keys_lo, const uint16_t *cnt, int64_t n,
                                   const void *bucket, int bits, int kmer, int64_t lo, int64_t hi,
                                   const SymmView &W, cudaStream_t st)
 { static int configured[64] = {0};                            /* per instantiation */
-  size_t smem = (size_t) RS_WIN*(8*KW+2) + (size_t) RS_STAGE*8*(KW+1) +
-                2*(size_t) (RS_TILE/2+RS_TILE/2);                                    /* 34 KB (k <= 32) / 55 KB */
   int dev = 0;
   cudaGetDevice(&dev);
-  if (smem > 48*1024 && (dev >= 64 || !configured[dev]))
-    { cudaError_t e = cudaFuncSetAttribute(runscan_kernel<IdxT,KW>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem);
-      if (e != cudaSuccess) return e;
-      if (dev < 64) configured[dev] = 1;
-    }
   int64_t tile0 = lo/RS_TILE, tile1 = (hi+RS_TILE-1)/RS_TILE;
   int     tma   = ((((uintptr_t) keys) | ((uintptr_t) cnt) | ((uintptr_t) (keys_lo ? keys_lo : keys))) & 15) == 0;
-  runscan_kernel<IdxT,KW><<<(unsigned) (tile1-tile0),RS_THREADS,smem,st>>>
-      (keys,keys_lo,cnt,n,(const IdxT *) bucket,64-bits,kmer,lo,hi,tile0,tma,W);
-  cudaError_t e = cudaGetLastError();
+  /* mean number of run mates of an entry = n / 4^(k/2): sparse tables take the classifying kernel, crowded
+   * ones the all-pairs-in-the-run kernel (HETMERS_RUNSCAN=sparse|dense forces one)                       */
+  const int   Pr  = kmer >> 1;
+  double      lam = (2*Pr >= 62) ? 0.0 : (double) n / (double) ((uint64_t) 1 << (2*Pr));
+  bool        dense = (lam > 0.6);
+  const char *force = getenv("HETMERS_RUNSCAN");
+  if (force != NULL && strcmp(force,"dense") == 0)  dense = true;
+  if (force != NULL && strcmp(force,"sparse") == 0) dense = false;
+  cudaError_t e;
+  if (dense)
+    { size_t smem = (size_t) RS_WIN*(8*KW+2) + (size_t) RS_STAGE*8*(KW+1) +
+                    2*(size_t) (RS_WIN+RS_TILE/8+RS_WIN) + 4*(size_t) (RS_WIN/2);   /* 43 KB (k <= 32) / 65 KB */
+      if (smem > 48*1024 && (dev >= 64 || !(configured[dev] & 2)))
+        { e = cudaFuncSetAttribute(runscan_dense_kernel<IdxT,KW>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem);
+          if (e != cudaSuccess) return e;
+          if (dev < 64) configured[dev] |= 2;
+        }
+      runscan_dense_kernel<IdxT,KW><<<(unsigned) (tile1-tile0),RS_THREADS,smem,st>>>
+          (keys,keys_lo,cnt,n,kmer,lo,hi,tile0,tma,W);
+    }
+  else
+    { size_t smem = (size_t) RS_WIN*(8*KW+2) + (size_t) RS_STAGE*8*(KW+1) +
+                    2*(size_t) (RS_TILE/2+RS_TILE/2);                                /* 34 KB (k <= 32) / 55 KB */
+      if (smem > 48*1024 && (dev >= 64 || !(configured[dev] & 1)))
+        { e = cudaFuncSetAttribute(runscan_kernel<IdxT,KW>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem);
+          if (e != cudaSuccess) return e;
+          if (dev < 64) configured[dev] |= 1;
+        }
+      runscan_kernel<IdxT,KW><<<(unsigned) (tile1-tile0),RS_THREADS,smem,st>>>
+          (keys,keys_lo,cnt,n,(const IdxT *) bucket,64-bits,kmer,lo,hi,tile0,tma,W);
+    }
+  e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   /* (building the Bloom filter from the record list in a kernel of its own instead of inside runscan_kernel
    *  was measured slower: +0.15 ms)                                                                        */

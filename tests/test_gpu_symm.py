@@ -21,6 +21,14 @@ def _need_gpu(built):
     assert _lib.lib().hm_device_count() >= 1, "these tests need a CUDA device (no CPU fallback exists)"
 
 
+@pytest.fixture(autouse=True, params=["sparse", "dense"])
+def runscan_kernel_variant(request, monkeypatch):
+    """pass 1 has two kernels, picked by the mean number of run mates n / 4^(k/2) (the classifying one for
+    sparse tables, all-pairs-in-the-run for crowded ones): every test runs with each of them forced"""
+    monkeypatch.setenv("HETMERS_RUNSCAN", request.param)
+    return request.param
+
+
 def _golden(name):
     return os.path.join(GOLDEN, name, name)
 
