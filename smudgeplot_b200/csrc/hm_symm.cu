@@ -769,6 +769,7 @@ runscan_dense_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restri
   S.t2r   = S.t1 + RS_WIN;                           /* here: heads of runs of more than RS_LONGRUN entries  */
   uint16_t *s_part = S.t2r + RS_TILE/8;               /* partner slot of every window slot (RS_WIN)           */
   unsigned *hu = (unsigned *) (s_part + RS_WIN);      /* partner counts: per slot H (low byte) | U (high byte) */
+  uint32_t *rem = hu + RS_WIN/2;                      /* k <= 32: the bases after the run prefix, 32 bits per slot */
 
   const int      Pr   = kmer >> 1, pup = kmer - Pr, psh = 64-2*Pr;
   const uint64_t pmask = ~(uint64_t) 0 << psh;
@@ -821,12 +822,16 @@ runscan_dense_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restri
   else
     mbar_wait(&s_bar,0);
 
-  /* ---- adjacency bits of the whole window ---- */
+  /* ---- adjacency bits of the whole window; k <= 32: the bases after the run prefix as one 32-bit word ---- */
+  const bool narrow = (KW == 1) && (kmer-Pr <= 16);      /* CTA-uniform: pair tests in 32-bit arithmetic */
   for (int wd = warp; wd < RS_WIN/32; wd += RS_THREADS/32)
     { const int i = wd*32 + lane;
       bool eq = false;
+      const uint64_t ki = S.key[i];
       if (i+1 < RS_WIN)
-        eq = (((S.key[i] ^ S.key[i+1]) & pmask) == 0);
+        eq = (((ki ^ S.key[i+1]) & pmask) == 0);
+      if (narrow)
+        rem[i] = (uint32_t) ((ki << (2*Pr)) >> 32);
       const unsigned bal = __ballot_sync(FULL,eq);
       if (lane == 0)
         s_eq[wd] = bal;
@@ -835,48 +840,62 @@ runscan_dense_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restri
     s_eq[RS_WIN/32] = 0;
   __syncthreads();
 
-  /* ---- every slot against the slots after it in its run ---- */
+  /* ---- run mates after / before every slot = consecutive ones in the adjacency bits (32 are in view) ---- */
   const int a0 = RS_HALO + (lo > T0 ? (int) (lo-T0 < RS_TILE ? lo-T0 : RS_TILE) : 0);   /* slots this CTA answers for */
   const int a1 = RS_HALO + (hi-T0 < RS_TILE ? (int) (hi-T0) : RS_TILE);
   for (int i = threadIdx.x; i < RS_WIN; i += RS_THREADS)
-    { /* members after / before slot i = consecutive ones in the adjacency bits (>= 33 of them are in view) */
-      const int      w = i >> 5, b = i & 31;
-      const uint64_t up = ((uint64_t) s_eq[w] | ((uint64_t) s_eq[w+1] << 32)) >> b;      /* eq[i], eq[i+1], ... */
-      const int      f  = __ffsll((long long) ~up);
-      const int      fwd = f ? f-1 : 64;
+    { const int      w = i >> 5, b = i & 31;
+      const unsigned up = __funnelshift_r(s_eq[w],s_eq[w+1],b);                 /* eq[i], eq[i+1], ... */
+      const int      fwd = (~up == 0) ? 32 : __ffs((int) ~up)-1;
       int back = 0;
       if (i > 0)
         { const int      wq = (i-1) >> 5, bq = (i-1) & 31;
-          const uint64_t dn = (((uint64_t) s_eq[wq] << 32) | (wq > 0 ? (uint64_t) s_eq[wq-1] : 0)) << (31-bq);
-          back = __clzll((long long) ~dn);                                                 /* eq[i-1], eq[i-2], ... from the top */
+          const unsigned dn = __funnelshift_l(wq > 0 ? s_eq[wq-1] : 0u,s_eq[wq],31-bq);   /* eq[i-1], eq[i-2], ... from the top */
+          back = (~dn == 0) ? 32 : __clz((int) ~dn);
         }
-      uint16_t mark = (uint16_t) i;                                                        /* "no partner yet" */
+      uint16_t mark = (uint16_t) fwd;                                            /* 0..31 run mates after this slot */
       if (back+fwd+1 > RS_LONGRUN)
-        { mark = 0xffff;                                                                   /* member of a long run: not ours */
-          if (back == 0 && i >= a0 && i < a1)                                              /* its head, in our range: runs_kernel */
+        { mark = 0xffff;                                                         /* member of a long run: not ours */
+          if (back == 0 && i >= a0 && i < a1)                                    /* its head, in our range: runs_kernel */
             S.t2r[atomicAdd(&s_nl,1u)] = (uint16_t) i;
         }
-      else if (fwd > 0)
-        mark = (uint16_t) (0x8000 | i);                                                    /* has run mates after it */
       S.t1[i] = mark;
+      s_part[i] = (uint16_t) i;
     }
   __syncthreads();
+
+  /* ---- every slot against the slots after it in its run ---- */
   for (int i = threadIdx.x; i < RS_WIN; i += RS_THREADS)
-    { if ((S.t1[i] & 0x8000) == 0 || S.t1[i] == 0xffff)
+    { const int fwd = S.t1[i];
+      if (fwd == 0 || fwd == 0xffff)
         continue;
-      const int      w = i >> 5, b = i & 31;
-      const uint64_t up = ((uint64_t) s_eq[w] | ((uint64_t) s_eq[w+1] << 32)) >> b;
-      const int      fwd = __ffsll((long long) ~up) - 1;
-      const uint64_t x = S.key[i], xl = KW == 2 ? S.klo[i] : 0;
-      const int      cx = S.cnt[i];
-      for (int j = i+1; j <= i+fwd; j++)
-        { int pos;
-          if (one_base_apart<KW>(x,xl,S.key[j],KW == 2 ? S.klo[j] : 0,pos) && cx + (int) S.cnt[j] <= HM_SMAX)
-            { const unsigned inc = 1u | (pos >= pup ? 0x100u : 0u);
-              atomicAdd(hu + (i>>1), inc << (16*(i&1)));
-              atomicAdd(hu + (j>>1), inc << (16*(j&1)));
-              s_part[i] = (uint16_t) j;                    /* any partner: only read when there is exactly one */
-              s_part[j] = (uint16_t) i;
+      const int cx = S.cnt[i];
+      if (narrow)
+        { const uint32_t rx = rem[i];
+          for (int j = i+1; j <= i+fwd; j++)
+            { const uint32_t d = rx ^ rem[j];
+              const uint32_t u = (d | (d>>1)) & 0x55555555u;
+              if ((u & (u-1)) == 0 && cx + (int) S.cnt[j] <= HM_SMAX)
+                { const int      pos = Pr + (__clz((int) d) >> 1);
+                  const unsigned inc = 1u | (pos >= pup ? 0x100u : 0u);
+                  atomicAdd(hu + (i>>1), inc << (16*(i&1)));
+                  atomicAdd(hu + (j>>1), inc << (16*(j&1)));
+                  s_part[i] = (uint16_t) j;                /* any partner: only read when there is exactly one */
+                  s_part[j] = (uint16_t) i;
+                }
+            }
+        }
+      else
+        { const uint64_t x = S.key[i], xl = KW == 2 ? S.klo[i] : 0;
+          for (int j = i+1; j <= i+fwd; j++)
+            { int pos;
+              if (one_base_apart<KW>(x,xl,S.key[j],KW == 2 ? S.klo[j] : 0,pos) && cx + (int) S.cnt[j] <= HM_SMAX)
+                { const unsigned inc = 1u | (pos >= pup ? 0x100u : 0u);
+                  atomicAdd(hu + (i>>1), inc << (16*(i&1)));
+                  atomicAdd(hu + (j>>1), inc << (16*(j&1)));
+                  s_part[i] = (uint16_t) j;
+                  s_part[j] = (uint16_t) i;
+                }
             }
         }
     }
@@ -970,7 +989,7 @@ static cudaError_t launch_runscan(const uint64_t *keys, const uint64_t *keys_lo,
   cudaError_t e;
   if (dense)
     { size_t smem = (size_t) RS_WIN*(8*KW+2) + (size_t) RS_STAGE*8*(KW+1) +
-                    2*(size_t) (RS_WIN+RS_TILE/8+RS_WIN) + 4*(size_t) (RS_WIN/2);   /* 43 KB (k <= 32) / 65 KB */
+                    2*(size_t) (RS_WIN+RS_TILE/8+RS_WIN) + 4*(size_t) (RS_WIN/2+RS_WIN);   /* 52 KB (k <= 32) / 74 KB */
       if (smem > 48*1024 && (dev >= 64 || !(configured[dev] & 2)))
         { e = cudaFuncSetAttribute(runscan_dense_kernel<IdxT,KW>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem);
           if (e != cudaSuccess) return e;
