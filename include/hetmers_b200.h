@@ -45,7 +45,7 @@ extern "C" {
 #define HM_ENOMEM       -3                  /* host or device allocation failed               */
 #define HM_EIO          -4                  /* cannot open / read a table file                */
 #define HM_EFORMAT      -5                  /* malformed FastK table                          */
-#define HM_EUNSUPPORTED -6                  /* valid input this build does not handle (k>32)  */
+#define HM_EUNSUPPORTED -6                  /* valid input this build does not handle (k>64)  */
 
 const char *hm_last_error(void);
 int         hm_abi_version(void);

@@ -406,7 +406,10 @@ __device__ __forceinline__ uint32_t *deg_words(const DegView &v, int64_t j)
   return v.peer[r];
 }
 
-/* book one qualifying pair (oi < j): both incidence bytes, and the upper partner of oi */
+/* book one qualifying pair (oi < j): both incidence bytes, and the upper partner of oi.  The bytes are
+ * packed four to a word and added to with word-wide atomics: no carry into the neighbouring byte as long
+ * as a degree stays below 256, i.e. 3k < 256 (the reference's uint8 Pair wraps instead, PloidyPlot.c:163) */
+static_assert(3*HM_MAX_KMER < 256,"byte-packed incidence counters would carry into their neighbours");
 template <typename IdxT>
 __device__ __forceinline__ void book_pair(const uint16_t *__restrict__ cnt, int64_t oi, int64_t j,
                                           int64_t lo, const DegView &dv, IdxT *__restrict__ up)

@@ -11,7 +11,8 @@
  *   peer_sum_plot_kernel  final reduction of the 1001x501 plot onto GPU 0; the reference does
  *                         this serially over its threads (PloidyPlot.c:1569-1575).
  *
- * Byte-packed adds cannot carry between bytes: a k-mer has at most 3k <= 96 neighbours (k<=32).
+ * Byte-packed adds cannot carry between bytes: a k-mer has at most 3k <= 192 < 256 neighbours (k <= 64;
+ * static_assert next to book_pair in hm_kernels.cu).
  * (The one-process-per-GPU variant uses NCCL through torch.distributed: smudgeplot_b200/dist.py.)
  *******************************************************************************************/
 #include <cuda_runtime.h>

@@ -86,7 +86,7 @@ def _cuda_view(ptr: int, nbytes: int, device) -> torch.Tensor:
 
 
 def allreduce_deg(deg: torch.Tensor, group=None):
-    """sum of the partial incidence arrays (uint8; no wrap: <= 3k <= 96 neighbours for k <= 32)"""
+    """sum of the partial incidence arrays (uint8; no wrap: <= 3k <= 192 neighbours for k <= 64)"""
     dist.all_reduce(deg, op=dist.ReduceOp.SUM, group=group)
     return deg
 
