@@ -304,9 +304,7 @@ def run_ours(args):
         if path == "symm":
             if events is not None:
                 events[0].record()
-            table.runscan()
-            if events is not None:
-                events[1].record()
+            table.runscan(mid_event=events[1] if events is not None else None)   # [0],[1] bracket runscan_kernel alone
             table.resolve()
             return table.plot
         table.deg.zero_()
@@ -353,8 +351,8 @@ def run_ours(args):
         ms_total, ms_p1 = t.tolist()
     ms_step = ms_total / args.steps
     value = nels / (ms_step * 1e-3)
-    # kernels of ours per scan: runscan + resolve (symmetric) / pass 1 + pass 2 (+ deferred look-ups, N > 1)
-    launches = (2 if (path == "symm" or not multi) else 3) * args.steps
+    # kernels of ours per scan: runscan + runs + resolve (symmetric) / pass 1 + pass 2 (+ deferred look-ups, N > 1)
+    launches = (3 if (path == "symm" or multi) else 2) * args.steps
 
     # ---- parity gates (untimed): the timed plot against independent computations of the same table ----
     parity = {"path": path}
@@ -384,7 +382,8 @@ def run_ours(args):
 
     peak, peak_src = peaks()
     per_launch = my_n
-    kname = "runscan_kernel" if path == "symm" else "pass1_filter_kernel"
+    kname = "runscan_kernel" if path == "symm" else "pass1_filter_kernel"       # (runscan_dense_kernel on crowded tables:
+                                                                                #  n / 4^(k/2) > 0.6, i.e. from N = 4 on)
     kbytes = TBYTE if path == "symm" else ALGO_BYTES_PER_KMER
     achieved = kbytes * per_launch / (ms_p1 * 1e-3) / 1e9
     whole = ALGO_BYTES_PER_KMER * nels / world / (ms_step * 1e-3) / 1e9

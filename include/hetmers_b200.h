@@ -181,10 +181,14 @@ void hm_symm_seeds(uint64_t seed[2]);       /* per-process random seeds for the 
 int  hm_k_symm_fingerprint(const uint64_t *d_keys, const uint64_t *d_keys_lo, const uint16_t *d_cnt,
                            int64_t i0, int64_t i1, int kmer, const uint64_t seed[2],
                            uint64_t *d_acc, void *stream);
-/* "pass 1": run scan of [lo,hi): Bloom segment `self` + candidate records (both initialised here).     */
+/* "pass 1": run scan of [lo,hi): Bloom segment `self` + candidate records (both initialised here), then
+ * hm_k_symm_runs for the runs it only listed (call both, in this order, on the same stream).            */
 int  hm_k_symm_runscan(const uint64_t *d_keys, const uint64_t *d_keys_lo, const uint16_t *d_cnt, int64_t n,
                        const void *d_bucket, int bits, int idx64, int kmer, int64_t lo, int64_t hi,
                        void *d_work, const hm_symm_layout *layout, const hm_symm_shards *shards, void *stream);
+int  hm_k_symm_runs(const uint64_t *d_keys, const uint64_t *d_keys_lo, const uint16_t *d_cnt, int64_t n,
+                    const void *d_bucket, int bits, int idx64, int kmer, int64_t lo, int64_t hi,
+                    void *d_work, const hm_symm_layout *layout, const hm_symm_shards *shards, void *stream);
 /* "pass 2": candidates -> isolated pairs -> d_plot (accumulated into; caller zeroes it)                 */
 int  hm_k_symm_resolve(const uint64_t *d_keys, const uint64_t *d_keys_lo, const uint16_t *d_cnt, int64_t n,
                        const void *d_bucket, int bits, int idx64, int kmer,

@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "hm_k_build_filter", "hm_filter_words", "hm_pick_filter_bits",
     "hm_dev_alloc", "hm_dev_free", "hm_ipc_export", "hm_ipc_open", "hm_ipc_close", "hm_p2p_native_atomics",
     "hm_scan_create", "hm_prewarm", "hm_set_io_threads", "hm_scan_destroy", "hm_scan_examine", "hm_scan_condition", "hm_scan_run", "hm_hetmers_host",
-    "hm_scan_run_path", "hm_scan_is_symmetric", "hm_symm_plan", "hm_symm_seeds", "hm_k_symm_fingerprint", "hm_k_symm_runscan", "hm_k_symm_resolve",
+    "hm_scan_run_path", "hm_scan_is_symmetric", "hm_symm_plan", "hm_symm_seeds", "hm_k_symm_fingerprint", "hm_k_symm_runscan", "hm_k_symm_runs", "hm_k_symm_resolve",
     "hm_symm_status", "hm_symm_align_cut",
     "hm_scan_download", "hm_table_open", "hm_table_close", "hm_table_view", "hm_write_smu",
 ]
@@ -124,6 +124,8 @@ def lib():
     L.hm_k_symm_fingerprint.argtypes = [vp, vp, vp, i64, i64, i32, C.POINTER(C.c_uint64), vp, vp]
     L.hm_k_symm_runscan.argtypes = [vp, vp, vp, i64, vp, i32, i32, i32, i64, i64, vp, C.POINTER(SymmLayout),
                                     C.POINTER(SymmShards), vp]
+    L.hm_k_symm_runs.argtypes = [vp, vp, vp, i64, vp, i32, i32, i32, i64, i64, vp, C.POINTER(SymmLayout),
+                                 C.POINTER(SymmShards), vp]
     L.hm_k_symm_resolve.argtypes = [vp, vp, vp, i64, vp, i32, i32, i32, vp, C.POINTER(SymmLayout),
                                     C.POINTER(SymmShards), vp, vp]
     L.hm_symm_status.argtypes = [vp, C.POINTER(SymmLayout), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), vp]

@@ -148,7 +148,11 @@ extern "C" void hm_scan_destroy(hm_scan *s)
 { if (s == NULL)
     return;
   for (int g = 0; g < s->ngpu; g++)
-    free_dev(s->d+g);
+    { int had_symm = (s->d[g].symm_work != NULL);
+      free_dev(s->d+g);
+      if (had_symm)                              /* hand the L2 lines the Bloom window made persisting back */
+        { cudaCtxResetPersistingL2Cache(); cudaGetLastError(); }
+    }
   free(s);
 }
 
@@ -907,8 +911,11 @@ static int run_symm(hm_scan *s, int64_t *plot, hm_scan_stats *stats, uint64_t *s
       HM_CUDA(cudaMemsetAsync(D->plot,0,sizeof(unsigned long long)*HM_PLOT_CELLS,D->st));
       rc = hm_k_symm_runscan(D->keys,D->keys_lo,D->cnt,n,D->bucket,s->bits,s->idx64,s->kmer,D->slo,D->shi,
                              D->symm_work,&D->symm_layout,G > 1 ? &s->ssh[g] : NULL,D->st);
+      if (rc == HM_OK)
+        rc = hm_k_symm_runs(D->keys,D->keys_lo,D->cnt,n,D->bucket,s->bits,s->idx64,s->kmer,D->slo,D->shi,
+                            D->symm_work,&D->symm_layout,G > 1 ? &s->ssh[g] : NULL,D->st);
       if (rc != HM_OK) return rc;
-      s->launches += (D->shi > D->slo);
+      s->launches += 2*(D->shi > D->slo);
       HM_CUDA(cudaEventRecord(ev[g][1],D->st));
     }
   if (G > 1)                                    /* every device pulls the other devices' Bloom segments */

@@ -225,9 +225,10 @@ extern "C" void hm_symm_seeds(uint64_t seed[2])
 extern "C" int hm_symm_plan(int64_t n, int64_t range, int kmer, int n_seg, hm_symm_layout *out)
 { if (out == NULL || n < 0 || range < 0 || range > n || n_seg < 1 || n_seg > HM_MAX_SHARDS)
     return hm_set_error(HM_EINVAL,"hm_symm_plan: bad arguments");
-  int bits = 1;                                  /* Bloom bits per table entry (S is ~1/6 of the table; two bits set per
-                                                  *   element): 25 MB at 2e8 entries.  2 bits: fewer exact checks in
-                                                  *   pass 2 (-0.15 ms) but the inserts of pass 1 miss L2 (+0.2 ms)   */
+  int bits = 2;                                  /* Bloom bits per table entry (S is ~1/6 of the table; two bits set per
+                                                  *   element): 50 MB at 2e8 entries, kept in L2 by an access-policy
+                                                  *   window (bloom_window).  Without the window its inserts miss L2 in
+                                                  *   pass 1 (+0.55 ms) and 1 bit per entry is the better choice        */
   const char *e = getenv("HETMERS_BLOOM_BITS");
   if (e != NULL && atoi(e) >= 1 && atoi(e) <= 64)
     bits = atoi(e);
@@ -253,6 +254,47 @@ extern "C" int hm_symm_plan(int64_t n, int64_t range, int kmer, int n_seg, hm_sy
   out->range = range;
   out->bytes = (at+255) & ~255ll;
   return HM_OK;
+}
+
+/* L2 residency of the Bloom segments for the kernels launched on `st` from here on: an access-policy window
+ * marks the filter "persisting" (its read-modify-writes in pass 1 and its look-ups in pass 2 then hit L2
+ * although 2 GB of table stream through next to them).  on = 0 lifts the window again.                   */
+static void bloom_window(cudaStream_t st, const void *base, size_t bytes, int on)
+{ static int limit_set[64] = {0};
+  static size_t max_win[64] = {0}, max_persist[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return;
+  if (!limit_set[dev])
+    { cudaDeviceProp p;
+      limit_set[dev] = 1;
+      if (cudaGetDeviceProperties(&p,dev) == cudaSuccess)
+        { max_win[dev] = (size_t) p.accessPolicyMaxWindowSize;
+          max_persist[dev] = (size_t) p.persistingL2CacheMaxSize;
+          if (max_persist[dev] > 0)
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize,max_persist[dev]);
+        }
+      cudaGetLastError();
+    }
+  if (max_win[dev] == 0 || max_persist[dev] == 0)
+    return;
+  cudaStreamAttrValue a;
+  memset(&a,0,sizeof(a));
+  if (on)
+    { size_t w = bytes < max_win[dev] ? bytes : max_win[dev];
+      a.accessPolicyWindow.base_ptr  = (void *) base;
+      a.accessPolicyWindow.num_bytes = w;
+      a.accessPolicyWindow.hitRatio  = w <= max_persist[dev] ? 1.0f : (float) max_persist[dev] / (float) w;
+      a.accessPolicyWindow.hitProp   = cudaAccessPropertyPersisting;
+      a.accessPolicyWindow.missProp  = cudaAccessPropertyStreaming;
+    }
+  cudaStreamSetAttribute(st,cudaStreamAttributeAccessPolicyWindow,&a);
+  cudaGetLastError();
+}
+
+static int l2_persist(void)                    /* HETMERS_L2_PERSIST=0 switches the window off */
+{ const char *e = getenv("HETMERS_L2_PERSIST");
+  return (e == NULL || strcmp(e,"0") != 0);
 }
 
 static SymmView make_view(void *d_work, const hm_symm_layout *L, const hm_symm_shards *sh)
@@ -1009,9 +1051,14 @@ static cudaError_t launch_runscan(const uint64_t *keys, const uint64_t *keys_lo,
       runscan_kernel<IdxT,KW><<<(unsigned) (tile1-tile0),RS_THREADS,smem,st>>>
           (keys,keys_lo,cnt,n,(const IdxT *) bucket,64-bits,kmer,lo,hi,tile0,tma,W);
     }
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  /* (building the Bloom filter from the record list in a kernel of its own instead of inside runscan_kernel
+  return cudaGetLastError();
+}
+
+template <typename IdxT, int KW>
+static cudaError_t launch_runs(const uint64_t *keys, const uint64_t *keys_lo, const uint16_t *cnt, int64_t n,
+                               const void *bucket, int bits, int kmer, int64_t lo, int64_t hi,
+                               const SymmView &W, cudaStream_t st)
+{ /* (building the Bloom filter from the record list in a kernel of its own instead of inside runscan_kernel
    *  was measured slower: +0.15 ms)                                                                        */
   int64_t want = ((hi-lo)/64+255)/256;                        /* ~1 run of three or more per 60 entries: a thread each */
   int     grid = (int) (want < 0x7fffffff ? (want > 0 ? want : 1) : 0x7fffffff);
@@ -1039,6 +1086,8 @@ extern "C" int hm_k_symm_runscan(const uint64_t *d_keys, const uint64_t *d_keys_
   SymmView W = make_view(d_work,layout,shards);
   HM_CUDA(cudaMemsetAsync(W.cand_n,0,256,st));
   HM_CUDA(cudaMemsetAsync(W.bloom + (size_t) W.self*W.seg_words,0,sizeof(uint32_t)*(size_t) W.seg_words,st));
+  if (l2_persist())
+    bloom_window(st,W.bloom,sizeof(uint32_t)*(size_t) W.seg_words*(size_t) W.n_seg,1);
   if (hi == lo)
     return HM_OK;
   cudaError_t e;
@@ -1050,6 +1099,31 @@ extern "C" int hm_k_symm_runscan(const uint64_t *d_keys, const uint64_t *d_keys_
               : launch_runscan<uint32_t,2>(d_keys,d_keys_lo,d_cnt,n,d_bucket,bits,kmer,lo,hi,W,st);
   if (e != cudaSuccess)
     return hm_cuda_fail(e,"runscan_kernel");
+  return HM_OK;
+}
+
+/* the runs runscan listed (three or more entries on sparse tables, more than RS_LONGRUN on crowded ones):
+ * second half of "pass 1", a launch of its own so that callers can time the dominant kernel alone      */
+extern "C" int hm_k_symm_runs(const uint64_t *d_keys, const uint64_t *d_keys_lo, const uint16_t *d_cnt, int64_t n,
+                              const void *d_bucket, int bits, int idx64, int kmer, int64_t lo, int64_t hi,
+                              void *d_work, const hm_symm_layout *layout, const hm_symm_shards *shards,
+                              void *stream)
+{ if (kmer < HM_SYMM_MIN_KMER || kmer > HM_MAX_KMER || d_work == NULL || layout == NULL ||
+      (kmer > 32) != (d_keys_lo != NULL) || lo < 0 || hi > n || lo > hi)
+    return hm_set_error(HM_EINVAL,"symm_runs: bad arguments");
+  if (hi == lo)
+    return HM_OK;
+  cudaStream_t st = (cudaStream_t) stream;
+  SymmView W = make_view(d_work,layout,shards);
+  cudaError_t e;
+  if (kmer <= 32)
+    e = idx64 ? launch_runs<uint64_t,1>(d_keys,NULL,d_cnt,n,d_bucket,bits,kmer,lo,hi,W,st)
+              : launch_runs<uint32_t,1>(d_keys,NULL,d_cnt,n,d_bucket,bits,kmer,lo,hi,W,st);
+  else
+    e = idx64 ? launch_runs<uint64_t,2>(d_keys,d_keys_lo,d_cnt,n,d_bucket,bits,kmer,lo,hi,W,st)
+              : launch_runs<uint32_t,2>(d_keys,d_keys_lo,d_cnt,n,d_bucket,bits,kmer,lo,hi,W,st);
+  if (e != cudaSuccess)
+    return hm_cuda_fail(e,"runs_kernel");
   return HM_OK;
 }
 
@@ -1292,6 +1366,8 @@ extern "C" int hm_k_symm_resolve(const uint64_t *d_keys, const uint64_t *d_keys_
   else
     e = idx64 ? launch_resolve<uint64_t,2>(d_keys,d_keys_lo,d_cnt,n,d_bucket,bits,kmer,W,d_plot,range,st)
               : launch_resolve<uint32_t,2>(d_keys,d_keys_lo,d_cnt,n,d_bucket,bits,kmer,W,d_plot,range,st);
+  if (l2_persist())
+    bloom_window(st,NULL,0,0);
   if (e != cudaSuccess)
     return hm_cuda_fail(e,"resolve_kernel");
   return HM_OK;

@@ -178,15 +178,18 @@ class DeviceTable:
         import ctypes as C
         return C.byref(self.symm_shards) if self.symm_shards is not None else None
 
-    def runscan(self):
-        """'pass 1' of the symmetric scan over [lo,hi)"""
+    def runscan(self, mid_event=None):
+        """'pass 1' of the symmetric scan over [lo,hi): runscan kernel, then the kernel for the runs it only
+        listed; `mid_event` is recorded between the two (timing of the dominant kernel alone)"""
         import ctypes as C
+        args = (_ptr(self.keys), _ptr(self.keys_lo), _ptr(self.cnt), self.n, _ptr(self.bucket), self.bits, self.idx64,
+                self.kmer, self.lo, self.hi, _ptr(self.symm_work), C.byref(self.symm_layout), self._symm_shards())
         with torch.cuda.device(self.device):
-            _lib.check(self.L.hm_k_symm_runscan(_ptr(self.keys), _ptr(self.keys_lo), _ptr(self.cnt), self.n,
-                                                _ptr(self.bucket), self.bits, self.idx64, self.kmer, self.lo, self.hi,
-                                                _ptr(self.symm_work), C.byref(self.symm_layout), self._symm_shards(),
-                                                _stream()))
-        self.launches += 1
+            _lib.check(self.L.hm_k_symm_runscan(*args, _stream()))
+            if mid_event is not None:
+                mid_event.record()
+            _lib.check(self.L.hm_k_symm_runs(*args, _stream()))
+        self.launches += 2
 
     def resolve(self):
         """'pass 2' of the symmetric scan; accumulates into self.plot"""

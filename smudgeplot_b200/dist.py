@@ -433,9 +433,7 @@ class ShardedScan:
         if events is not None:
             events[0].record()
         if ph: ph[0].record()
-        t.runscan()
-        if events is not None:
-            events[1].record()
+        t.runscan(mid_event=events[1] if events is not None else None)   # [0],[1]: the dominant kernel alone
         if ph: ph[1].record()
         if self.world > 1:
             exchange_segments(t.bloom_view(), self.rank, self.group)
