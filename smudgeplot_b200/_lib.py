@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libhetmers_b200.so")
+LIB_PATH = os.environ.get("HETMERS_LIB") or os.path.join(HERE, "lib", "libhetmers_b200.so")   # (override: tuning builds)
 BIN_PATH = os.path.join(HERE, "bin", "hetmers")
 
 SMAX, FMAX = 1000, 500

@@ -52,9 +52,13 @@
 #define RS_SCANCAP RS_HALO                     /* longest run half scanned linearly               */
 #define RS_LONGRUN 32                          /* dense kernel: runs of more entries go to runs_kernel */
 #ifndef RS_MINBLOCKS
-#define RS_MINBLOCKS 5                         /* resident CTAs per SM the register budget must allow          */
+#define RS_MINBLOCKS 6                         /* resident CTAs per SM the register budget must allow (40 regs;
+                                                *   4: 1.18 ms, 5: 1.07, 6 with 30 KB of shared memory: 0.99)     */
 #endif
-#define RS_STAGE   512                         /* candidate records staged per CTA before they leave */
+#ifndef RS_STAGE
+#define RS_STAGE   384                         /* candidate records staged per CTA before they leave (a 2048-entry
+                                                *   tile of a diploid 1 % table holds 184 +- 14)                    */
+#endif
 
 #define SY_STATUS_ASYMMETRIC 1ull              /* a reverse complement was not in the table      */
 #define SY_STATUS_OVERFLOW   2ull              /* candidate list full                             */
@@ -229,6 +233,10 @@ extern "C" int hm_symm_plan(int64_t n, int64_t range, int kmer, int n_seg, hm_sy
                                                   *   element): 50 MB at 2e8 entries, kept in L2 by an access-policy
                                                   *   window (bloom_window).  Without the window its inserts miss L2 in
                                                   *   pass 1 (+0.55 ms) and 1 bit per entry is the better choice        */
+  if (n_seg > 1)                                 /* several GPUs: all segments together are far beyond L2 and have to
+                                                  *   cross NVLink between the kernels (0.95 ms of a 4.6 ms scan at 8
+                                                  *   GPUs with 2 bits): half the filter, a few more exact checks      */
+    bits = 1;
   const char *e = getenv("HETMERS_BLOOM_BITS");
   if (e != NULL && atoi(e) >= 1 && atoi(e) <= 64)
     bits = atoi(e);
@@ -357,7 +365,8 @@ __device__ __forceinline__ void stage_one(const RsSmem<KW> &S, unsigned *s_nc, c
     }
 }
 
-/* warp-wide variant: one shared atomic for all the lanes that emit */
+/* warp-wide variant: one shared atomic for all the lanes that emit; lanes that find the staging area full
+ * go to the list directly, again with one (global) atomic for all of them                              */
 template <int KW>
 __device__ __forceinline__ void stage_candidates(const RsSmem<KW> &S, unsigned *s_nc, const SymmView &W,
                                                  bool emit, uint64_t x, uint64_t xl, uint64_t meta,
@@ -369,20 +378,25 @@ __device__ __forceinline__ void stage_candidates(const RsSmem<KW> &S, unsigned *
   if (lane == 0)
     base = atomicAdd(s_nc,(unsigned) __popc(bal));
   base = __shfl_sync(0xffffffffu,base,0);
-  if (!emit)
-    return;
-  unsigned at = base + __popc(bal & lt);
-  if (at < RS_STAGE)
+  const unsigned at = base + __popc(bal & lt);
+  const bool     over = emit && (at >= RS_STAGE);
+  if (emit && !over)
     { S.ckey[at] = x;
       if (KW == 2) S.clo[at] = xl;
       S.cmeta[at] = meta;
     }
-  else
-    { unsigned long long g1 = atomicAdd(W.cand_n,1ull);
-      if (g1 < W.cand_cap)
-        { W.cand_key[g1] = x;
-          if (KW == 2) W.cand_lo[g1] = xl;
-          W.cand_meta[g1] = meta;
+  if (base + __popc(bal) <= RS_STAGE)                  /* (warp-uniform) nobody overflowed */
+    return;
+  const unsigned ob = __ballot_sync(0xffffffffu,over);
+  unsigned long long g0 = 0;
+  if (lane == 0)
+    g0 = atomicAdd(W.cand_n,(unsigned long long) __popc(ob));
+  g0 = __shfl_sync(0xffffffffu,g0,0) + (unsigned long long) __popc(ob & lt);
+  if (over)
+    { if (g0 < W.cand_cap)
+        { W.cand_key[g0] = x;
+          if (KW == 2) W.cand_lo[g0] = xl;
+          W.cand_meta[g0] = meta;
         }
       else
         atomicOr(W.status,SY_STATUS_OVERFLOW);

@@ -252,3 +252,25 @@ def test_symmetric_scan_repeats_and_bloom_width(monkeypatch):
         t = DeviceTable(31, keys, c16).build_index(direct=False)
         assert torch.equal(t.scan("symm"), want), bits
         assert torch.equal(t.scan("symm"), want), bits
+
+
+def test_tables_made_of_pairs_overflow_the_record_staging(tmp_path):
+    """nearly every entry is a member of an isolated pair: ~1000 candidate records per 2048-entry tile, far
+    beyond the per-CTA staging area (RS_STAGE = 384) -> the warp-aggregated direct path to the list"""
+    rng = np.random.default_rng(4242)
+    k = 31
+    base = rng.integers(0, 1 << 62, size=30000, dtype=np.int64).astype(np.uint64)
+    base = (base >> np.uint64(2)) << np.uint64(2)                      # k = 31: the last two bits are padding
+    pos = rng.integers(k // 2, k, size=base.size)                      # partner: one base changed in the back half
+    sh = (np.uint64(62) - np.uint64(2) * pos.astype(np.uint64))
+    delta = rng.integers(1, 4, size=base.size).astype(np.uint64)
+    mate = base ^ (delta << sh)
+    keys, cnt = _symmetric_closure(np.concatenate([base, mate]), k, rng, 60)
+    kt = fastk.write_ktab(str(tmp_path / "t"), k, keys, cnt, ibyte=3, nparts=2)
+    want_plot, want_deg = ou.oracle_scan(fastk.keys_u64_to_bytes(keys, k), cnt, k)
+    assert (want_deg == 1).mean() > 0.9
+    with hetmers.Scan(kt) as sc:
+        assert sc.is_symmetric()
+        plot, st = sc.run("symm")
+    assert st["path"] == 2
+    assert np.array_equal(plot, want_plot)
