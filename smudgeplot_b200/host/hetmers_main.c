@@ -16,6 +16,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <stdarg.h>
 #include <unistd.h>
 #include <strings.h>
 
@@ -67,6 +68,26 @@ static void systemx(const char *command)                         /* SystemX, gen
     { fprintf(stderr,"%s: Command '%s' failed\n",Prog_Name,command);
       exit (1);
     }
+}
+
+/* format a command line into `buf` (sized by the caller for the longest one) and run it */
+static void run_tool(char *buf, const char *fmt, ...)
+{ va_list ap;
+  va_start(ap,fmt);
+  vsprintf(buf,fmt,ap);
+  va_end(ap);
+  systemx(buf);
+}
+
+/* the reference's -v progress line for a conditioning step: 't' = trim, 's' = symmetrise */
+static void announce_step(int verbose, int step, int was_trimmed, int ethresh)
+{ if (!verbose)
+    return;
+  if (step == 't')
+    fprintf(stderr,"\n  Trimming k-mers in table with count < %d\n",ethresh);
+  else
+    fprintf(stderr,was_trimmed ? "\n  Making table symmetric\n" : "\n  Making trimmed table symmetric\n");
+  fflush(stderr);
 }
 
 static void die_hm(void)
@@ -381,17 +402,16 @@ int main(int argc, char *argv[])
 
     sprintf(tname,"%s",SRC);
 
-    if ((!trim || !symm) && getenv("HETMERS_EXTERNAL_CONDITIONING") == NULL)
+    if (trim && symm)
+      { free(command);                 //  nothing to do: the table is scanned as it is
+        free(tname);
+      }
+    else if (getenv("HETMERS_EXTERNAL_CONDITIONING") == NULL)
       { //  Condition the table where it already is -- on the GPU -- instead of shelling out to
         //  FastK's Logex / Symmex and re-reading their output (same progress lines with -v)
         int64_t nn;
-        if (VERBOSE)
-          { if (!trim)
-              fprintf(stderr,"\n  Trimming k-mers in table with count < %d\n",ETHRESH);
-            if (!symm)
-              fprintf(stderr,trim ? "\n  Making table symmetric\n" : "\n  Making trimmed table symmetric\n");
-            fflush(stderr);
-          }
+        if (!trim) announce_step(VERBOSE,'t',trim,ETHRESH);
+        if (!symm) announce_step(VERBOSE,'s',trim,ETHRESH);
         if (hm_scan_condition(S,ETHRESH,!trim,!symm,&nn) != HM_OK)
           die_hm();
         if (nn < 2)
@@ -402,37 +422,31 @@ int main(int argc, char *argv[])
         free(tname);
       }
     else
-      {
-    if (!trim)
-      { if (VERBOSE)
-          { fprintf(stderr,"\n  Trimming k-mers in table with count < %d\n",ETHRESH);
-            fflush(stderr);
-          }
-        sprintf(command,"Logex -T%d '%s.trim=A[%d-]' %s",NTHREADS,troot,ETHRESH,tname);
-        systemx(command);
-        sprintf(tname,"%s.trim",troot);
-      }
-
-    if (!symm)
-      { if (VERBOSE)
-          { if (trim)
-              fprintf(stderr,"\n  Making table symmetric\n");
-            else
-              fprintf(stderr,"\n  Making trimmed table symmetric\n");
-            fflush(stderr);
-          }
-        sprintf(command,"Symmex -T%d -P%s %s %s.symx",NTHREADS,SORT_PATH,tname,troot);
-        systemx(command);
+      { //  Compatibility shim (HETMERS_EXTERNAL_CONDITIONING=1): hand the table to FastK's own tools as the
+        //  reference does (PloidyPlot.c:1381-1426) -- same command lines, so the same files appear -- and load
+        //  whatever they leave behind.
+        const char *made = NULL;
         if (!trim)
-          { sprintf(command,"Fastrm %s.trim",troot);
-            systemx(command);
+          { announce_step(VERBOSE,'t',trim,ETHRESH);
+            run_tool(command,"Logex -T%d '%s.trim=A[%d-]' %s",NTHREADS,troot,ETHRESH,tname);
+            made = ".trim";
           }
-        sprintf(tname,"%s.symx",troot);
-      }
-
-    free(command);
-    if (!(symm && trim))
-      { input = tname;
+        if (!symm)
+          { char *from = malloc(strlen(tname)+strlen(troot)+10);
+            announce_step(VERBOSE,'s',trim,ETHRESH);
+            if (from == NULL)
+              exit (1);
+            if (made != NULL) sprintf(from,"%s%s",troot,made);
+            else              strcpy(from,tname);
+            run_tool(command,"Symmex -T%d -P%s %s %s.symx",NTHREADS,SORT_PATH,from,troot);
+            if (made != NULL)
+              run_tool(command,"Fastrm %s.trim",troot);
+            free(from);
+            made = ".symx";
+          }
+        free(command);
+        sprintf(tname,"%s%s",troot,made);
+        input = tname;
         hm_scan_destroy(S);
         hm_table_close(T);
         if (hm_table_open(input,&T) != HM_OK)
@@ -441,9 +455,6 @@ int main(int argc, char *argv[])
           }
         if (hm_scan_create(hm_table_view(T),devs,ngpu,&S) != HM_OK)
           die_hm();
-      }
-    else
-      free(tname);
       }
   }
 
