@@ -155,6 +155,13 @@ unpack_records_kernel(const uint8_t *__restrict__ rec, int64_t n, int64_t first,
  * Needs a 16-byte aligned source (tile size UNP_TILE*pbyte is a multiple of 16 by construction). */
 #define UNP_TILE 1024
 
+#define UNP_MAXSPAN 16384          /* stub-index buckets a tile may span before records bisect on their own */
+
+/* The prefix of a record is the stub-index bucket its ordinal falls into.  Records and buckets are both in
+ * order, so a tile resolves its prefixes together: every NON-EMPTY bucket that starts inside the tile marks
+ * its first record (the tile spans ~90 buckets at 2e8 k-mers: one coalesced pass over that slice of the
+ * index), and a max-scan over the 1024 marks hands every record the last bucket that started at or before
+ * it.  (One global-memory bisection per record, ~7 dependent loads each, held the kernel at 17 % of HBM.) */
 __global__ void __launch_bounds__(256)
 unpack_records_tma_kernel(const uint8_t *__restrict__ rec, int64_t first,
                           const int64_t *__restrict__ index, int ixlen, int ibyte, int hbyte,
@@ -163,31 +170,74 @@ unpack_records_tma_kernel(const uint8_t *__restrict__ rec, int64_t first,
 { extern __shared__ __align__(128) uint8_t s_rec[];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_blo, s_bhi;
+  __shared__ int s_mark[UNP_TILE];
+  __shared__ int s_wmax[8];
   const int      pbyte = hbyte+2;
   const unsigned bytes = (unsigned) (UNP_TILE*pbyte);
   const int64_t  t0    = (int64_t) blockIdx.x * UNP_TILE;
+  const int64_t  base  = first+t0;                       /* table ordinal of the tile's first record */
 
   if (threadIdx.x == 0)
     { mbar_init(&s_bar,1);
       fence_proxy_async_smem();
     }
+  for (int r = threadIdx.x; r < UNP_TILE; r += 256)
+    s_mark[r] = 0;
   __syncthreads();
   if (threadIdx.x == 0)
     { mbar_arrive_expect_tx(&s_bar,bytes);
       bulk_copy_g2s(s_rec,rec + t0*pbyte,bytes,&s_bar);
-      s_blo = upper_bound_index(index,0,ixlen-1,first+t0);              /* overlaps the copy */
-      s_bhi = upper_bound_index(index,s_blo,ixlen-1,first+t0+UNP_TILE-1);
+      s_blo = upper_bound_index(index,0,ixlen-1,base);                  /* overlaps the copy */
+      s_bhi = upper_bound_index(index,s_blo,ixlen-1,base+UNP_TILE-1);
     }
   __syncthreads();
+  const int  blo = s_blo, bhi = s_bhi;
+  const bool together = (bhi-blo <= UNP_MAXSPAN);        /* CTA-uniform */
+  int pre[UNP_TILE/256];
+  if (together)
+    { /* bucket b covers ordinals [index[b-1], index[b]); blo holds the tile's first record */
+      for (int b = blo+1+threadIdx.x; b <= bhi; b += 256)
+        { const int64_t s0 = __ldg(index+b-1), s1 = __ldg(index+b);
+          if (s1 > s0)                                   /* non-empty: starts inside the tile (blo < b <= bhi) */
+            s_mark[(int) (s0-base)] = b;
+        }
+      __syncthreads();
+      /* inclusive max-scan of the marks: 4 consecutive records per thread, then warps, then the CTA */
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      int m = blo;
+#pragma unroll
+      for (int k = 0; k < UNP_TILE/256; k++)
+        { const int v = s_mark[threadIdx.x*(UNP_TILE/256)+k];
+          if (v > m) m = v;
+          pre[k] = m;
+        }
+      int run = m;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+        { const int v = __shfl_up_sync(0xffffffffu,run,o);
+          if (lane >= o && v > run) run = v;
+        }
+      if (lane == 31) s_wmax[warp] = run;
+      __syncthreads();
+      int before = blo;                                   /* max of everything in earlier threads */
+      for (int w = 0; w < warp; w++)
+        if (s_wmax[w] > before) before = s_wmax[w];
+      const int prev = __shfl_up_sync(0xffffffffu,run,1);
+      if (lane > 0 && prev > before) before = prev;
+      __syncthreads();                                     /* everybody has read the marks: reuse them for the result */
+#pragma unroll
+      for (int k = 0; k < UNP_TILE/256; k++)
+        s_mark[threadIdx.x*(UNP_TILE/256)+k] = before > pre[k] ? before : pre[k];
+      __syncthreads();
+    }
   mbar_wait(&s_bar,0);
 
-  const int blo = s_blo, bhi = s_bhi;
 #pragma unroll
   for (int k = 0; k < UNP_TILE/256; k++)
-    { const int      r = threadIdx.x + 256*k;
+    { const int      r = threadIdx.x + 256*k;              /* consecutive lanes, consecutive records: coalesced stores */
       const int64_t  i = t0+r;
       const uint8_t *q = s_rec + r*pbyte;
-      uint64_t b = (uint64_t) upper_bound_index(index,blo,bhi,first+i);
+      uint64_t b = together ? (uint64_t) s_mark[r] : (uint64_t) upper_bound_index(index,blo,bhi,first+i);
       uint64_t key = b << (64-8*ibyte), klo = 0;
       for (int j = 0; j < hbyte; j++)
         { int pos = ibyte+j;
