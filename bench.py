@@ -159,13 +159,13 @@ def time_reference(table, nels, threads, runs=1):
     ora = os.path.join(ROOT, "oracle", "hetmers_oracle")
     out = os.path.join(os.path.dirname(table), "cpu_out")
     times = []
+    if os.path.exists(ref):
+        cmd, kind = [ref, f"-e{LCUT}", f"-T{threads}", f"-o{out}", table], "reference"
+    else:
+        cmd, kind = [ora, f"-e{LCUT}", f"-o{out}", table], "port"
     for _ in range(runs):
         if os.path.exists(out + ".smu"):
             os.remove(out + ".smu")
-        if os.path.exists(ref):
-            cmd, kind = [ref, f"-e{LCUT}", f"-T{threads}", f"-o{out}", table], "reference"
-        else:
-            cmd, kind = [ora, f"-e{LCUT}", f"-o{out}", table], "port"
         t0 = time.perf_counter()
         r = subprocess.run(cmd, input="n\n", capture_output=True, text=True)
         times.append(time.perf_counter() - t0)
@@ -181,14 +181,12 @@ def cpu_sample_size(args, threads):
     return int(max(2e6, min(n, args.nels)))
 
 
-def bench_config(world, nels=None, extra=None):
-    """the `config` object both arms print (same keys, same workload)"""
-    c = {"workload": workload_name(world), "k": K, "ploidy": PLOIDY, "het": HET, "cov": COV, "L": LCUT, "seed": SEED}
-    if nels is not None:
-        c["nels"] = nels
-    if extra:
-        c.update(extra)
-    return c
+def bench_config(world):
+    """the `config` object BOTH arms print: the workload and nothing run-specific (what a run did with it is
+    in the line's `run` object; the reference arm's bounded sample in `cpu_baseline.sample`)"""
+    return {"workload": workload_name(world), "k": K, "ploidy": PLOIDY, "het": HET, "cov": COV, "L": LCUT, "seed": SEED,
+            "target_nels_per_gpu": 2e8,
+            "l2": "inputs (>= 1.9 GB table + bucket index per GPU) exceed the 126 MB L2; no flush between iterations"}
 
 
 def run_reference_arm(args):
@@ -391,11 +389,10 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": bench_config(world, nels, {
-                "nels_per_gpu": my_n, "bucket_bits": table.bits, "scan": path,
-                "parallelism": (f"table replica per GPU, {world} contiguous run-aligned index shards; exchange: {job.exchange}"
-                                if multi else "1 GPU"),
-                "l2": "inputs (>=1.9 GB table + bucket index per GPU) exceed the 126 MB L2; no flush between iterations"}),
+            "config": bench_config(world),
+            "run": {"nels": nels, "nels_per_gpu": my_n, "bucket_bits": table.bits, "scan": path,
+                    "parallelism": (f"table replica per GPU, {world} contiguous run-aligned index shards; exchange: {job.exchange}"
+                                    if multi else "1 GPU")},
             "clocks": clk.summary(), "gpu_launches": launches, "parity": parity,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
@@ -410,7 +407,7 @@ def run_ours(args):
         allp = [None] * world
         dist.all_gather_object(allp, {k: round(v, 3) for k, v in job.phase_ms().items()})
         names = list(allp[0].keys())                                   # one compact list per phase, all ranks
-        line["config"]["phases_ms_by_rank"] = {nm: [a[nm] for a in allp] for nm in names if nm != "-"}
+        line["run"]["phases_ms_by_rank"] = {nm: [a[nm] for a in allp] for nm in names if nm != "-"}
     if e2e is not None:
         line["e2e"] = e2e
         if multi and "plot_matches_resident_scan" in e2e:
