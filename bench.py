@@ -380,8 +380,10 @@ def run_ours(args):
 
     peak, peak_src = peaks()
     per_launch = my_n
-    kname = "runscan_kernel" if path == "symm" else "pass1_filter_kernel"       # (runscan_dense_kernel on crowded tables:
-                                                                                #  n / 4^(k/2) > 0.6, i.e. from N = 4 on)
+    # pass 1 of the symmetric scan has two kernels: the launcher takes the all-pairs-in-the-run one when an entry
+    # has more than 0.6 run mates on average (n / 4^(k/2): from N = 4 on in this weak-scaling series)
+    dense = os.environ.get("HETMERS_RUNSCAN", "dense" if nels / float(4 ** (K // 2)) > 0.6 else "sparse") == "dense"
+    kname = ("runscan_dense_kernel" if dense else "runscan_kernel") if path == "symm" else "pass1_filter_kernel"
     kbytes = TBYTE if path == "symm" else ALGO_BYTES_PER_KMER
     achieved = kbytes * per_launch / (ms_p1 * 1e-3) / 1e9
     whole = ALGO_BYTES_PER_KMER * nels / world / (ms_step * 1e-3) / 1e9
@@ -398,7 +400,7 @@ def run_ours(args):
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "algorithmic_bytes_per_kmer": kbytes, "ms_per_launch": ms_p1,
                          "traffic": measured_traffic(kname, per_launch, grid),
-                         "note": ("runscan_kernel reads every entry (8 B key + 2 B count) exactly once; the second kernel "
+                         "note": (kname + " reads every entry (8 B key + 2 B count) exactly once; the second kernel "
                                   "reads candidate records only.  whole_scan = SURVEY §8d's official 22 B/k-mer over T_scan"
                                   if path == "symm" else "22 B/k-mer = SURVEY §8d (two passes)"),
                          "whole_scan": {"algorithmic_bytes_per_kmer": ALGO_BYTES_PER_KMER, "achieved": whole,
