@@ -21,9 +21,13 @@
  *                             direct search of hm_kernels.cu, so the answer is the reference's
  *                             either way.
  *   runscan_kernel            ("pass 1") tiles of the sorted table are staged into shared memory by
- *                             TMA bulk copies; every entry scans its run: H, U, its partner.
+ *                             TMA bulk copies; entries are classified by the adjacency of their
+ *                             runs, runs of two are settled by one comparison (H, U, the partner).
  *                             Entries with U > 0 (the set S) are added to a Bloom filter; pairs
  *                             (x < y) with H(x) = H(y) = 1 become candidate records.
+ *   runs_kernel               the runs of three or more entries that runscan_kernel only lists
+ *   runscan_dense_kernel      pass 1 for crowded tables (many run mates per entry): all pairs of
+ *                             every run, counted with shared-memory atomics
  *   resolve_kernel            ("pass 2") a candidate is an isolated pair iff neither rc x nor rc y
  *                             is in S: Bloom look-up (L2 resident), hits confirmed exactly by
  *                             scanning the run of rc x in the table.  Isolated pairs are counted
@@ -343,29 +347,8 @@ template <int KW> struct RsSmem
 __device__ __forceinline__ uint64_t pack_meta(int cx, int cy, int pos, int yb)
 { return (uint64_t) cx | ((uint64_t) cy << 16) | ((uint64_t) pos << 32) | ((uint64_t) yb << 40); }
 
-/* one candidate record into the CTA's staging area (any lane, no collective) */
-template <int KW>
-__device__ __forceinline__ void stage_one(const RsSmem<KW> &S, unsigned *s_nc, const SymmView &W,
-                                          uint64_t x, uint64_t xl, uint64_t meta)
-{ unsigned at = atomicAdd(s_nc,1u);
-  if (at < RS_STAGE)
-    { S.ckey[at] = x;
-      if (KW == 2) S.clo[at] = xl;
-      S.cmeta[at] = meta;
-    }
-  else                                               /* staging full (dense tables): straight to the list */
-    { unsigned long long g1 = atomicAdd(W.cand_n,1ull);
-      if (g1 < W.cand_cap)
-        { W.cand_key[g1] = x;
-          if (KW == 2) W.cand_lo[g1] = xl;
-          W.cand_meta[g1] = meta;
-        }
-      else
-        atomicOr(W.status,SY_STATUS_OVERFLOW);
-    }
-}
-
-/* warp-wide variant: one shared atomic for all the lanes that emit; lanes that find the staging area full
+/* candidate records into the CTA's staging area (warp-wide call; `emit` per lane): one shared atomic for
+ * all the lanes that emit; lanes that find the staging area full
  * go to the list directly, again with one (global) atomic for all of them                              */
 template <int KW>
 __device__ __forceinline__ void stage_candidates(const RsSmem<KW> &S, unsigned *s_nc, const SymmView &W,
