@@ -151,7 +151,12 @@ int hm_k_pass2_extract(const uint64_t *d_keys, const uint64_t *d_keys_lo, const 
  * sit in one short run of neighbouring entries.  hm_k_symm_runscan + hm_k_symm_resolve produce the
  * same plot as hm_k_pass1_degree + hm_k_pass2_plot (= the reference's two passes) on such a table;
  * hm_k_symm_fingerprint decides whether a table is one (keyed multiset fingerprints of {(x,cnt)}
- * and {(rc x,cnt)}: acc[0]==acc[2] && acc[1]==acc[3]); anything else must take the direct passes. */
+ * and {(rc x,cnt)}: acc[0]==acc[2] && acc[1]==acc[3]); anything else must take the direct passes.
+ * Replaces, for such tables: analysis_in_core_1/_2 + analysis_thread_1/_2 and the window / recursion
+ * drivers around them (PloidyPlot.c:168-700,:712-1084); the fingerprint extends examine_table's
+ * one-k-mer symmetry probe (PloidyPlot.c:1199-1229) to the whole table.
+ * Side effect: hm_k_symm_runscan puts an access-policy window (persisting L2 lines) over the Bloom
+ * filter on `stream` and hm_k_symm_resolve lifts it again (HETMERS_L2_PERSIST=0 disables it).      */
 #define HM_SYMM_MIN_KMER 2
 
 typedef struct hm_symm_layout               /* work area of one scan range (hm_symm_plan fills it in)     */
