@@ -4,6 +4,7 @@ contract (PloidyPlot.c:1246-1314,1350-1354; gene_core.h:32-56) for the cases tha
 import os
 import re
 import subprocess
+import sys
 
 import pytest
 
@@ -207,3 +208,68 @@ def test_layer_c_smu_writer_matches_oracle_writer(built, tmp_path):
     assert "500\t500\t" not in text
     rows = [tuple(int(v) for v in ln.split("\t")) for ln in text.splitlines()]
     assert rows == sorted(rows, key=lambda r: (r[0] + r[1], r[0]))   # sum-major, then min (PloidyPlot.c:1612)
+
+
+# ---- strand-symmetric scan: host-side pieces of the C ABI (no GPU needed) -------------------------
+
+def test_symm_plan_layout_invariants(built):
+    import ctypes as C
+    from smudgeplot_b200 import _lib
+    L = _lib.lib()
+    for n, rng, k, seg in ((2, 2, 31, 1), (200_000_000, 200_000_000, 31, 1), (1_600_000_000, 200_000_000, 31, 8),
+                           (5_000_000_000, 625_000_000, 40, 8), (1000, 0, 21, 2)):
+        lay = _lib.SymmLayout()
+        assert L.hm_symm_plan(n, rng, k, seg, C.byref(lay)) == 0
+        assert lay.n_seg == seg and lay.range == rng
+        assert lay.cand_cap >= rng // 2 + 1 and lay.runs_cap >= rng // 3 + 1
+        assert lay.seg_words >= 1024 and lay.seg_words % 64 == 0
+        assert lay.seg_words * 32 * seg >= n                    # at least one filter bit per table entry in all
+        # regions in order, non-overlapping, 8-byte aligned, inside `bytes`
+        regs = [(lay.off_header, 256), (lay.off_bloom, 4 * lay.seg_words * seg), (lay.off_cand_key, 8 * lay.cand_cap)]
+        if k > 32:
+            regs.append((lay.off_cand_lo, 8 * lay.cand_cap))
+        regs += [(lay.off_cand_meta, 8 * lay.cand_cap), (lay.off_runs, 8 * lay.runs_cap)]
+        end = 0
+        for off, size in regs:
+            assert off % 8 == 0 and off >= end
+            end = off + size
+        assert end <= lay.bytes and lay.bytes % 256 == 0
+    lay = _lib.SymmLayout()
+    assert L.hm_symm_plan(10, 20, 31, 1, C.byref(lay)) == -1    # range > n
+    assert L.hm_symm_plan(10, 5, 31, 0, C.byref(lay)) == -1     # no segment
+    assert L.hm_symm_plan(10, 5, 31, _lib.MAX_SHARDS + 1, C.byref(lay)) == -1
+    assert b"hm_symm_plan" in L.hm_last_error()
+
+
+def test_symm_bloom_bits_env_and_multi_gpu_default(built, monkeypatch):
+    """one GPU: 2 filter bits per entry (held in L2 by the access-policy window); several GPUs: 1 (the segments
+    cross NVLink); HETMERS_BLOOM_BITS overrides both"""
+    import ctypes as C
+    from smudgeplot_b200 import _lib
+    L = _lib.lib()
+    monkeypatch.delenv("HETMERS_BLOOM_BITS", raising=False)
+    one, many = _lib.SymmLayout(), _lib.SymmLayout()
+    n = 64_000_000
+    assert L.hm_symm_plan(n, n, 31, 1, C.byref(one)) == 0 and L.hm_symm_plan(8 * n, n, 31, 8, C.byref(many)) == 0
+    assert one.seg_words * 32 >= 2 * n and one.seg_words * 32 < 2 * n + 64 * 32
+    assert many.seg_words * 32 >= n and many.seg_words * 32 < n + 64 * 32
+    monkeypatch.setenv("HETMERS_BLOOM_BITS", "5")
+    five = _lib.SymmLayout()
+    assert L.hm_symm_plan(n, n, 31, 1, C.byref(five)) == 0 and five.seg_words * 32 >= 5 * n
+
+
+def test_symm_seeds_are_drawn_once_per_process(built):
+    import ctypes as C
+    from smudgeplot_b200 import _lib
+    L = _lib.lib()
+    a, b = (C.c_uint64 * 2)(), (C.c_uint64 * 2)()
+    L.hm_symm_seeds(a)
+    L.hm_symm_seeds(b)
+    assert (a[0], a[1]) == (b[0], b[1]) and (a[0] != 0 or a[1] != 0) and a[0] != a[1]
+    r = subprocess.run([sys.executable, "-c",
+                        "import sys; sys.path.insert(0, %r); import ctypes as C; from smudgeplot_b200 import _lib; "
+                        "s = (C.c_uint64 * 2)(); _lib.lib().hm_symm_seeds(s); print(s[0], s[1])" % ROOT],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    other = tuple(int(v) for v in r.stdout.split())
+    assert other != (a[0], a[1])                                # another process, other seeds
